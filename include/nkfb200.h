@@ -1,0 +1,198 @@
+/*
+ * nkfb200 -- C ABI of the B200-native (sm_100a) hot path of netket_fidelity:
+ * one infidelity-gradient step of p-tVMC.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers/sizes and a
+ * `cudaStream_t` (passed as void*), returns 0 on success or a negative
+ * NKFB_ERR_* code, never throws and never calls exit().  Device memory is owned
+ * by the caller (the Python host passes `tensor.data_ptr()`); the library only
+ * reads/writes through those pointers on `stream`.  The only library-owned
+ * memory is the per-handle workspace used by the *_host entry points.
+ *
+ * Each declaration cites the reference interface it replaces
+ * (paths relative to the netket_fidelity repository).
+ *
+ * Data layouts
+ *  - configurations ("samples") are bit-packed: uint32 words, W32 = ceil(N/32)
+ *    words per configuration, site i -> bit (i & 31) of word (i >> 5);
+ *    bit 0 <-> local_states[0], bit 1 <-> local_states[1]
+ *    (Spin(1/2): -1 / +1, Qubit: 0 / 1).
+ *  - RBM parameters are complex, interleaved (re, im), in the real type named
+ *    by `dtype` (NKFB_F32 -> complex64, NKFB_F64 -> complex128):
+ *    kernel (N, M) row-major (the NetKet `Dense/kernel` leaf), bias (M),
+ *    visible_bias (N).  Real-parameter RBMs are passed with zero imaginary
+ *    parts; their gradient is the real part of the complex-convention one.
+ *  - flat gradient / accumulator layout: [bias (M) | kernel (N*M) | visible_bias (N)],
+ *    complex, i.e. the leaf order of jax.tree_util on the NetKet RBM parameter dict.
+ */
+#ifndef NKFB200_H
+#define NKFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NKFB_VERSION 100
+
+enum {
+  NKFB_OK = 0,
+  NKFB_ERR_INVALID = -1,     /* bad argument */
+  NKFB_ERR_UNSUPPORTED = -2, /* shape / mode outside what the kernels cover */
+  NKFB_ERR_CUDA = -3,        /* a CUDA runtime call failed; see nkfb_last_error */
+  NKFB_ERR_NOMEM = -4
+};
+
+enum { NKFB_F32 = 0, NKFB_F64 = 1 };
+
+enum { NKFB_OP_NONE = 0, NKFB_OP_GATE = 1, NKFB_OP_ISING = 2 };
+
+typedef struct nkfb_handle_s *nkfb_handle_t;
+
+/* RBM parameters (NetKet nk.models.RBM; verbatim form in
+ * examples/twospins_GHZ/RBM_Jastrow_ansatz.py:37-62). */
+typedef struct {
+  int32_t n_visible;        /* N */
+  int32_t n_hidden;         /* M = alpha N */
+  int32_t dtype;            /* NKFB_F32 | NKFB_F64 */
+  int32_t reserved;
+  const void *kernel;       /* device, (N, M) complex */
+  const void *bias;         /* device, (M) complex, or NULL (use_hidden_bias=False) */
+  const void *visible_bias; /* device, (N) complex, or NULL (use_visible_bias=False) */
+} nkfb_rbm_t;
+
+/* A discrete operator given by its connected elements.
+ *  GATE : any single-site operator (Rx, Ry, Hadamard:
+ *         netket_fidelity/operator/singlequbit_gates.py:89-105,184-201,270-288).
+ *         conn 0 = x, conn 1 = x with site `idx` flipped;
+ *         mel[c] = gate_mel[bit of x at idx][c] (re, im).
+ *  ISING: conn 0 = x with mel = c0 + c1 * sum_<ij> (2[x_i==x_j]-1);
+ *         conn i+1 = x with site i flipped, mel = c2   (NetKet IsingJax,
+ *         netket_fidelity/operator/__init__.py:4; propagator 1 - i dt H likewise). */
+typedef struct {
+  int32_t kind; /* NKFB_OP_* */
+  int32_t idx;
+  double gate_mel[2][2][2];
+  double c0[2], c1[2], c2[2];
+  int32_t n_edges;
+  int32_t reserved;
+  const int32_t *edges; /* device, (n_edges, 2) */
+} nkfb_op_t;
+
+typedef struct {
+  int64_t n_chains;      /* chains handled by THIS call (this rank's shard) */
+  int32_t chain_length;  /* samples emitted per chain */
+  int32_t n_discard;     /* sweeps discarded before the first emitted sample */
+  int32_t sweep_size;    /* MH steps per sweep (NetKet default: N) */
+  int32_t site_mode;     /* 0: one site sequence shared by all chains; 1: per-chain sites (NetKet) */
+  uint64_t seed;
+  uint64_t chain_offset; /* global id of this call's first chain (multi-GPU sharding) */
+  uint64_t step_offset;  /* MH steps already consumed by earlier calls (Philox counter offset) */
+  double local_states[2];
+  int32_t init_random;   /* !=0: ignore chain_state on input, start from Philox-random configurations */
+  int32_t reserved;
+} nkfb_sample_cfg_t;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int nkfb_version(void);
+int nkfb_create(int device, nkfb_handle_t *out);
+int nkfb_destroy(nkfb_handle_t h);
+const char *nkfb_last_error(nkfb_handle_t h);
+/* number of kernels this handle has launched so far (bench.py: gpu_launches) */
+int64_t nkfb_launch_count(nkfb_handle_t h);
+
+/* ---- configurations <-> packed bits ------------------------------------- */
+/* x: device (B, N) of dtype NKFB_F32/NKFB_F64 holding local-state values. */
+int nkfb_pack(nkfb_handle_t h, const void *x, int x_dtype, int64_t B, int N,
+              const double local_states[2], uint32_t *packed, void *stream);
+int nkfb_unpack(nkfb_handle_t h, const uint32_t *packed, int64_t B, int N,
+                const double local_states[2], void *x, int x_dtype, void *stream);
+
+/* ---- connected elements (materialising) --------------------------------- */
+/* Replaces Rx/Ry/Hadamard.get_conn_padded (singlequbit_gates.py:65-71,160-166,250-256)
+ * and IsingJax.get_conn_padded.  x (B,N) -> xp (B,C,N) same dtype, mels (B,C) complex128.
+ * C = 2 (GATE) or N+1 (ISING).  Bit-exact target. */
+int nkfb_conn(nkfb_handle_t h, const nkfb_op_t *op, const void *x, int x_dtype,
+              int64_t B, int N, const double local_states[2], void *xp, void *mels,
+              void *stream);
+
+/* ---- log-amplitudes ------------------------------------------------------ */
+/* out[b] = log sum_c mel_c psi(x'_c)  (op == NULL or NONE: log psi(x)).
+ * Replaces afun(variables, x) of nk.models.RBM and _logpsi_U_fun
+ * (netket_fidelity/utils/sampling_Ustate.py:34-47).  out: (B) complex of net->dtype. */
+int nkfb_logpsi(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
+                const uint32_t *packed, int64_t B, const double local_states[2],
+                void *out, void *stream);
+
+/* ---- Metropolis-local sampler ------------------------------------------- */
+/* Replaces nk.sampler.MetropolisLocal + MCState.samples/reset (call sites
+ * infidelity/overlap/expect.py:26-27, overlap_U/expect.py:21-22,
+ * driver/infidelity_optimizer.py:142-143).  Target density |sum_c mel_c psi(x'_c)|^2.
+ * chain_state: device (n_chains, W32) in/out.  samples: device
+ * (n_chains, chain_length, W32).  n_accepted: device uint64[1] (accumulated) or NULL. */
+int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
+                const nkfb_sample_cfg_t *cfg, uint32_t *chain_state, uint32_t *samples,
+                unsigned long long *n_accepted, void *stream);
+
+/* ---- infidelity estimator (pass A) -------------------------------------- */
+/* Replaces kernel_fun of infidelity_sampling_MCState
+ * (infidelity/overlap/expect.py:78-89, overlap_U/expect.py:101-120):
+ *   l_s = T(phi,sigma_s;op1) + T(psi,eta_s;op2) - T(psi,sigma_s) - T(phi,eta_s;op4)
+ *   L_s = Re e^{l_s} + cv (e^{2 Re l_s} - 1)          (cv = NaN <-> cv_coeff None)
+ * Outputs (device): log_val (S) complex, L (S) real, rho1 (S) complex (weight of the
+ * flipped connected element of op2, 0 if op2 is NONE), all of psi->dtype;
+ * sums: double[8] ACCUMULATED: [sum L, sum L^2, sum |A|^2, sum Re A, S, 0, 0, 0]. */
+int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
+                        const nkfb_op_t *op1, const nkfb_op_t *op2, const nkfb_op_t *op4,
+                        const uint32_t *sigma, const uint32_t *eta, int64_t S,
+                        const double local_states[2], double cv_coeff, void *log_val,
+                        void *L, void *rho1, double *sums, void *stream);
+
+/* ---- infidelity gradient (pass B) --------------------------------------- */
+/* Replaces nkjax.expect's backward + nkjax.vjp(conjugate=True)
+ * (infidelity/overlap/expect.py:103-125, overlap_U/expect.py:134-156), closed form:
+ *   acc_k += sum_s [ w_sig conj O_k(sigma_s) + w_eta conj D_k(eta_s) ],
+ *   w_eta = conj A + 2 cv |A|^2,  w_sig = 2 (L_s - F) - w_eta,  F = sums[0]/sums[4]
+ * (sums must already hold the GLOBAL sums, i.e. after the scalar all-reduce).
+ * grad_acc: device double[2*(M + N*M + N)], complex128 accumulators in the flat layout. */
+int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2,
+                         const uint32_t *sigma, const uint32_t *eta, int64_t S,
+                         const double local_states[2], double cv_coeff,
+                         const void *log_val, const void *rho1, const double *sums,
+                         double *grad_acc, void *stream);
+
+/* I_grad = -acc / sums[4], cast to `dtype` (infidelity/overlap/expect.py:126-127).
+ * grad_out: device (P) complex of `dtype`, flat layout. */
+int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums,
+                       int64_t P, int dtype, void *grad_out, void *stream);
+
+/* ---- chain statistics ---------------------------------------------------- */
+/* Partial sums needed by nk.stats.statistics on data viewed as (rows, cols):
+ * per row: [sum, sum of first half, sum of second half] and `n_blocks` block sums of
+ * length l_block.  L: device (rows*cols) real of `dtype`.  out: device double
+ * [rows * (3 + n_blocks)]. */
+int nkfb_chain_stats(nkfb_handle_t h, const void *L, int dtype, int64_t rows, int64_t cols,
+                     int64_t l_block, int64_t n_blocks, double *out, void *stream);
+
+/* ---- Renyi-2 swap estimator --------------------------------------------- */
+/* Replaces netket.experimental.observable.Renyi2EntanglementEntropy on MCState
+ * (netket_fidelity/renyi2.py:1).  samples (2*S_half, W32): first half sigma, second half
+ * sigma'.  mask: device (W32) bit i set <-> site i in the partition.
+ * q (S_half) complex of net->dtype; sums double[8] accumulated:
+ * [sum Re q, sum (Re q)^2, sum Im q, S_half, ...]. */
+int nkfb_renyi2(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *samples,
+                int64_t S_half, const uint32_t *mask, const double local_states[2],
+                uint32_t *scratch /* device (2*S_half, W32) */, void *scratch_logpsi /* device (4*S_half) complex */,
+                void *q, double *sums, void *stream);
+
+/* ---- MUFU / FP32 micro-benchmarks (roofline denominators) ---------------- */
+/* Runs `iters` dependent-free MUFU.EX2 (kind 0), MUFU.COS (1), MUFU.LG2 (2) or FFMA (3)
+ * per thread on a full grid; returns operations/second measured with CUDA events. */
+int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops_per_second, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NKFB200_H */

@@ -1,0 +1,620 @@
+// Metropolis-local sampler kernels.
+//
+// Plain RBM target (|psi|^2): a group of L lanes owns C Markov chains; lane l of the group
+// holds the hidden pre-activations theta_j, j = l + L k (k < K <= KMAX), of each of its
+// chains in registers and applies the incremental update theta += (x_new - x_old) W[i, :]
+// for a single-site flip instead of a from-scratch forward.  The acceptance ratio needs
+// only Re log cosh:  log2|cosh(x+iy)| = |x| log2(e) - 1 + 1/2 log2(1 + t^2 + 2 t cos 2y),
+// t = 2^(-2 log2(e) |x|), i.e. MUFU.EX2 + MUFU.COS per hidden unit and one MUFU.LG2 per
+// four units (the arguments of the logs are multiplied first).  Random numbers come from
+// Philox4x32-10 keyed by the seed with (step block, global chain id, stream tag) as
+// counter, so results do not depend on how chains are sharded over GPUs.
+//
+// Composite target (|sum_c mel_c phi(x'_c)|^2, c over the connected elements of a gate or
+// of an Ising-type operator): one warp per chain, complex log cosh for every connected
+// configuration of the proposal.
+#include <cstdio>
+#include <cstring>
+
+#include "tile.cuh"
+
+namespace nkfb {
+
+enum { TAG_UNIFORM = 0, TAG_SITE_CHAIN = 1, TAG_SITE_SHARED = 2, TAG_INIT = 3 };
+
+struct SampArgs {
+  int64_t n_chains;
+  int chain_length, n_discard, sweep_size, site_mode, init_random;
+  uint32_t k0, k1;
+  uint64_t chain_offset, step_offset;
+  double s0, s1;
+  uint32_t *chain_state, *samples;
+  unsigned long long *n_accepted;
+  OpDev op;
+};
+
+template <typename R>
+struct SMath;
+template <>
+struct SMath<float> {
+  // returns the log2-domain pieces: adds |x| to sumabs, multiplies prod by (1 + t^2 + 2 t cos 2y)
+  static __device__ __forceinline__ void unit(float x, float y, float &sumabs, float &prod) {
+    const float ax = fabsf(x);
+    const float t = mufu_ex2(ax * (float)(-2.0 * LOG2E));
+    const float c = mufu_cos(2.0f * y);
+    prod *= fmaf(t, fmaf(2.0f, c, t), 1.0f);
+    sumabs += ax;
+  }
+  static __device__ __forceinline__ float flush(float &prod) {
+    float r = mufu_lg2(prod);
+    prod = 1.0f;
+    return r;
+  }
+  static __device__ __forceinline__ float finish(float sumabs, float lg) {
+    return fmaf(sumabs, (float)LOG2E, 0.5f * lg);
+  }
+  static __device__ __forceinline__ float log2u(uint32_t r) {
+    return mufu_lg2(((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f));
+  }
+};
+template <>
+struct SMath<double> {
+  static __device__ __forceinline__ void unit(double x, double y, double &sumabs, double &prod) {
+    const double ax = fabs(x);
+    const double t = exp(-2.0 * ax);
+    const double c = cos(2.0 * y);
+    prod *= fma(t, fma(2.0, c, t), 1.0);
+    sumabs += ax;
+  }
+  static __device__ __forceinline__ double flush(double &prod) {
+    double r = log2(prod);
+    prod = 1.0;
+    return r;
+  }
+  static __device__ __forceinline__ double finish(double sumabs, double lg) { return fma(sumabs, LOG2E, 0.5 * lg); }
+  static __device__ __forceinline__ double log2u(uint32_t r) { return log2(((double)r + 0.5) * (1.0 / 4294967296.0)); }
+};
+
+template <int L, typename T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+  for (int m = L / 2; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t sel4(const u32x4 &v, int c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+constexpr int SAMP_WARPS = 4;
+
+// =====================================================================================
+template <typename R, int L, int KMAX, int C>
+__global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R> net, SampArgs a) {
+  constexpr int G = 32 / L;      // chain groups per warp
+  constexpr int NCH = G * C;     // chains per warp
+  constexpr int BLK = 32 / NCH;  // Philox blocks per chain per batch
+  constexpr int SB = 4 * BLK;    // MH steps per RNG batch
+  extern __shared__ uint32_t sig_all[];
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / L, l = lane % L;
+  const int K = (M + L - 1) / L;
+  uint32_t *sig = sig_all + (size_t)warp * NCH * W32;  // [NCH][W32]
+  const int64_t warp_global = (int64_t)blockIdx.x * SAMP_WARPS + warp;
+  const int64_t chain0 = warp_global * NCH;  // first local chain of this warp
+  if (chain0 >= a.n_chains) return;
+  const R s0 = (R)a.s0, s1 = (R)a.s1, ssum = s0 + s1;
+
+  // ---- load / initialise configurations
+  for (int idx = lane; idx < NCH * W32; idx += 32) {
+    const int slot = idx / W32, w = idx - slot * W32;
+    const int64_t ch = chain0 + slot;
+    uint32_t v = 0;
+    if (ch < a.n_chains) {
+      if (a.init_random) {
+        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + ch), (uint32_t)TAG_INIT};
+        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+      } else {
+        v = a.chain_state[ch * W32 + w];
+      }
+      const int nb = N - 32 * w;
+      if (nb < 32) v &= (1u << nb) - 1u;
+    }
+    sig[idx] = v;
+  }
+  __syncwarp();
+
+  // ---- theta from scratch
+  R thr[C][KMAX], thi[C][KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = l + L * k;
+    R br = R(0), bi = R(0);
+    if (k < K && j < M && net.b) {
+      br = net.b[2 * j];
+      bi = net.b[2 * j + 1];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      thr[c][k] = br;
+      thi[c][k] = bi;
+    }
+  }
+  for (int i = 0; i < N; ++i) {
+    R xv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) xv[c] = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = l + L * k;
+      if (k < K && j < M) {
+        const R wr = net.W[2 * ((int64_t)i * M + j)], wi = net.W[2 * ((int64_t)i * M + j) + 1];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          thr[c][k] = fma(xv[c], wr, thr[c][k]);
+          thi[c][k] = fma(xv[c], wi, thi[c][k]);
+        }
+      }
+    }
+  }
+  R lc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    R sumabs = R(0), prod = R(1), lg = R(0);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K && l + L * k < M) SMath<R>::unit(thr[c][k], thi[c][k], sumabs, prod);
+      if ((k & 3) == 3) lg += SMath<R>::flush(prod);
+    }
+    lc[c] = group_sum<L>(SMath<R>::finish(sumabs, lg));
+  }
+
+  unsigned n_acc = 0;
+  const int total_sweeps = a.n_discard + a.chain_length;
+  uint64_t step = a.step_offset;  // global MH step index (multiple of SB is NOT required)
+  u32x4 ru = {0, 0, 0, 0}, rs = {0, 0, 0, 0};
+  R lu[4] = {R(0), R(0), R(0), R(0)};
+  uint64_t batch_base = ~0ull;  // first step covered by the current RNG batch
+
+  for (int sweep = 0; sweep < total_sweeps; ++sweep) {
+    for (int t = 0; t < a.sweep_size; ++t, ++step) {
+      // ---- refill the RNG batch: lane r serves chain slot r % NCH, Philox block r / NCH
+      const uint64_t bb = step - (step % SB);
+      if (bb != batch_base) {
+        batch_base = bb;
+        const uint64_t blk = bb / 4 + (uint64_t)(lane / NCH);
+        const uint32_t chid = (uint32_t)(a.chain_offset + chain0 + (lane % NCH));
+        u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
+        ru = philox4x32_10(ctr, a.k0, a.k1);
+        lu[0] = SMath<R>::log2u(ru.x);
+        lu[1] = SMath<R>::log2u(ru.y);
+        lu[2] = SMath<R>::log2u(ru.z);
+        lu[3] = SMath<R>::log2u(ru.w);
+        if (a.site_mode == 0) {
+          const uint64_t sblk = bb / 4 + (uint64_t)(lane % BLK);
+          u32x4 c2 = {(uint32_t)sblk, (uint32_t)(sblk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
+          rs = philox4x32_10(c2, a.k0, a.k1);
+        } else {
+          ctr.w = (uint32_t)TAG_SITE_CHAIN;
+          rs = philox4x32_10(ctr, a.k0, a.k1);
+        }
+      }
+      const int tb = (int)(step - batch_base);  // 0 .. SB-1
+      const int bi = tb >> 2, comp = tb & 3;
+      const uint32_t my_rs = sel4(rs, comp);
+      const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
+
+      int site_shared = 0;
+      R wr[KMAX], wi[KMAX];
+      R ar_shared = R(0);
+      if (a.site_mode == 0) {
+        site_shared = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int j = l + L * k;
+          wr[k] = R(0);
+          wi[k] = R(0);
+          if (k < K && j < M) {
+            wr[k] = net.W[2 * ((int64_t)site_shared * M + j)];
+            wi[k] = net.W[2 * ((int64_t)site_shared * M + j) + 1];
+          }
+        }
+        if (net.a) ar_shared = net.a[2 * site_shared];
+      }
+
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const int src = slot + NCH * bi;
+        const R logu = __shfl_sync(0xffffffffu, my_lu, src);
+        int site = site_shared;
+        R ar = ar_shared;
+        if (a.site_mode != 0) {
+          site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const int j = l + L * k;
+            wr[k] = R(0);
+            wi[k] = R(0);
+            if (k < K && j < M) {
+              wr[k] = net.W[2 * ((int64_t)site * M + j)];
+              wi[k] = net.W[2 * ((int64_t)site * M + j) + 1];
+            }
+          }
+          ar = net.a ? net.a[2 * site] : R(0);
+        }
+        const uint32_t word = sig[slot * W32 + (site >> 5)];
+        const R xold = ((word >> (site & 31)) & 1u) ? s1 : s0;
+        const R d = ssum - R(2) * xold;  // x_new - x_old
+        R sumabs = R(0), prod = R(1), lg = R(0);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) SMath<R>::unit(fma(d, wr[k], thr[c][k]), fma(d, wi[k], thi[c][k]), sumabs, prod);
+          if ((k & 3) == 3) lg += SMath<R>::flush(prod);
+        }
+        const R lcn = group_sum<L>(SMath<R>::finish(sumabs, lg));
+        // log2 of the acceptance ratio |psi(x')|^2 / |psi(x)|^2
+        const R dl = R(2) * (lcn - lc[c]) + R(2.0 * LOG2E) * d * ar;
+        const bool acc = (logu < dl) && (chain0 + slot < a.n_chains);
+        const R de = acc ? d : R(0);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) {
+            thr[c][k] = fma(de, wr[k], thr[c][k]);
+            thi[c][k] = fma(de, wi[k], thi[c][k]);
+          }
+        }
+        lc[c] = acc ? lcn : lc[c];
+        if (acc && l == 0) {
+          sig[slot * W32 + (site >> 5)] = word ^ (1u << (site & 31));
+          ++n_acc;
+        }
+      }
+      __syncwarp();
+    }
+    if (sweep >= a.n_discard) {
+      const int ts = sweep - a.n_discard;
+      for (int idx = lane; idx < NCH * W32; idx += 32) {
+        const int slot = idx / W32, w = idx - slot * W32;
+        const int64_t ch = chain0 + slot;
+        if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w] = sig[idx];
+      }
+    }
+  }
+  for (int idx = lane; idx < NCH * W32; idx += 32) {
+    const int slot = idx / W32, w = idx - slot * W32;
+    const int64_t ch = chain0 + slot;
+    if (ch < a.n_chains) a.chain_state[ch * W32 + w] = sig[idx];
+  }
+  if (a.n_accepted) {
+    n_acc = warp_sum(n_acc);
+    if (lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+  }
+}
+
+// =====================================================================================
+// Composite target: log Phi(x) = log sum_c mel_c(x) phi(x'_c).  One warp per chain.
+template <typename R>
+__device__ __forceinline__ cx<R> warp_csum(cx<R> v) {
+  v.re = warp_sum(v.re);
+  v.im = warp_sum(v.im);
+  return v;
+}
+
+// log Phi of the configuration in `sg` whose pre-activations are (thr, thi) and a.x = ax
+template <typename R, int KMAX>
+__device__ __forceinline__ cx<R> composite_logamp(const NetDev<R> &net, const OpDev &op, const uint32_t *sg,
+                                                  const R (&thr)[KMAX], const R (&thi)[KMAX], cx<R> ax, int K,
+                                                  R s0, R s1) {
+  const int N = net.N, M = net.M;
+  const int lane = threadIdx.x & 31;
+  const R ssum = s0 + s1;
+  cx<R> base = mk<R>(0, 0);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K && lane + 32 * k < M) base = base + lncosh(mk<R>(thr[k], thi[k]));
+  base = warp_csum(base) + ax;
+  if (op.kind == NKFB_OP_GATE) {
+    const int idx = op.idx;
+    const int bit = (sg[idx >> 5] >> (idx & 31)) & 1u;
+    const R d = ssum - R(2) * (bit ? s1 : s0);
+    cx<R> fl = mk<R>(0, 0);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = lane + 32 * k;
+      if (k < K && j < M) {
+        const R wr = net.W[2 * ((int64_t)idx * M + j)], wi = net.W[2 * ((int64_t)idx * M + j) + 1];
+        fl = fl + lncosh(mk<R>(fma(d, wr, thr[k]), fma(d, wi, thi[k])));
+      }
+    }
+    fl = warp_csum(fl) + ax;
+    if (net.a) fl = fl + d * mk<R>(net.a[2 * idx], net.a[2 * idx + 1]);
+    const cx<R> m0 = mk<R>((R)op.gate_mel[bit][0][0], (R)op.gate_mel[bit][0][1]);
+    const cx<R> m1 = mk<R>((R)op.gate_mel[bit][1][0], (R)op.gate_mel[bit][1][1]);
+    const R amax = fmax(base.re, fl.re);
+    const cx<R> sum = m0 * cexp(mk<R>(base.re - amax, base.im)) + m1 * cexp(mk<R>(fl.re - amax, fl.im));
+    cx<R> T = clog(sum);
+    T.re += amax;
+    return T;
+  }
+  // ISING: neighbours k = 0..N-1; lane (k % 32) keeps the amplitude of neighbour k in a small ring
+  // (processed in rounds of 32 neighbours, online log-sum-exp across rounds)
+  R zz = R(0);
+  for (int e = lane; e < op.n_edges; e += 32) {
+    const int ia = op.edges[2 * e], ib = op.edges[2 * e + 1];
+    const int ba = (sg[ia >> 5] >> (ia & 31)) & 1u, bb = (sg[ib >> 5] >> (ib & 31)) & 1u;
+    zz += (ba == bb) ? R(1) : R(-1);
+  }
+  zz = warp_sum(zz);
+  const cx<R> mdiag = mk<R>((R)op.c0[0] + (R)op.c1[0] * zz, (R)op.c0[1] + (R)op.c1[1] * zz);
+  const cx<R> moff = mk<R>((R)op.c2[0], (R)op.c2[1]);
+  R run_max = base.re;
+  cx<R> run_sum = mdiag * cexp(mk<R>(R(0), base.im));  // in units of exp(run_max)
+  for (int k0 = 0; k0 < N; k0 += 32) {
+    cx<R> mine = mk<R>(-INFINITY, 0);
+    const int kend = min(32, N - k0);
+    for (int kk = 0; kk < kend; ++kk) {
+      const int k = k0 + kk;
+      const int bit = (sg[k >> 5] >> (k & 31)) & 1u;
+      const R d = ssum - R(2) * (bit ? s1 : s0);
+      cx<R> fl = mk<R>(0, 0);
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q) {
+        const int j = lane + 32 * q;
+        if (q < K && j < M) {
+          const R wr = net.W[2 * ((int64_t)k * M + j)], wi = net.W[2 * ((int64_t)k * M + j) + 1];
+          fl = fl + lncosh(mk<R>(fma(d, wr, thr[q]), fma(d, wi, thi[q])));
+        }
+      }
+      fl = warp_csum(fl) + ax;
+      if (net.a) fl = fl + d * mk<R>(net.a[2 * k], net.a[2 * k + 1]);
+      if (lane == kk) mine = fl;
+    }
+    R mx = mine.re;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    const R new_max = fmax(run_max, mx);
+    cx<R> part = mk<R>(0, 0);
+    if (lane < kend) part = moff * cexp(mk<R>(mine.re - new_max, mine.im));
+    part = warp_csum(part);
+    const R sc = exp_(run_max - new_max);
+    run_sum = mk<R>(run_sum.re * sc + part.re, run_sum.im * sc + part.im);
+    run_max = new_max;
+  }
+  cx<R> T = clog(run_sum);
+  T.re += run_max;
+  return T;
+}
+
+template <typename R, int KMAX>
+__global__ void __launch_bounds__(SAMP_WARPS * 32) sample_composite_kernel(NetDev<R> net, SampArgs a) {
+  extern __shared__ uint32_t sig_all[];
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = (M + 31) / 32;
+  uint32_t *sg = sig_all + (size_t)warp * W32;
+  const int64_t ch = (int64_t)blockIdx.x * SAMP_WARPS + warp;
+  if (ch >= a.n_chains) return;
+  const R s0 = (R)a.s0, s1 = (R)a.s1, ssum = s0 + s1;
+  const OpDev &op = a.op;  // read from the kernel arguments; no block-level sync is used
+
+  for (int w = lane; w < W32; w += 32) {
+    uint32_t v;
+    if (a.init_random) {
+      u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + ch), (uint32_t)TAG_INIT};
+      v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+    } else {
+      v = a.chain_state[ch * W32 + w];
+    }
+    const int nb = N - 32 * w;
+    if (nb < 32) v &= (1u << nb) - 1u;
+    sg[w] = v;
+  }
+  __syncwarp();
+
+  R thr[KMAX], thi[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = lane + 32 * k;
+    thr[k] = (k < K && j < M && net.b) ? net.b[2 * j] : R(0);
+    thi[k] = (k < K && j < M && net.b) ? net.b[2 * j + 1] : R(0);
+  }
+  cx<R> ax = mk<R>(0, 0);
+  for (int i = 0; i < N; ++i) {
+    const R x = ((sg[i >> 5] >> (i & 31)) & 1u) ? s1 : s0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = lane + 32 * k;
+      if (k < K && j < M) {
+        thr[k] = fma(x, net.W[2 * ((int64_t)i * M + j)], thr[k]);
+        thi[k] = fma(x, net.W[2 * ((int64_t)i * M + j) + 1], thi[k]);
+      }
+    }
+    if (net.a) ax = ax + x * mk<R>(net.a[2 * i], net.a[2 * i + 1]);
+  }
+  R logp = R(2) * composite_logamp<R, KMAX>(net, op, sg, thr, thi, ax, K, s0, s1).re;
+
+  unsigned n_acc = 0;
+  const int total_sweeps = a.n_discard + a.chain_length;
+  uint64_t step = a.step_offset;
+  const uint32_t chid = (uint32_t)(a.chain_offset + ch);
+  for (int sweep = 0; sweep < total_sweeps; ++sweep) {
+    for (int t = 0; t < a.sweep_size; ++t, ++step) {
+      const uint64_t blk = step >> 2;
+      const int comp = (int)(step & 3);
+      u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
+      const uint32_t r_u = sel4(philox4x32_10(ctr, a.k0, a.k1), comp);
+      if (a.site_mode == 0) {
+        ctr.z = 0u;
+        ctr.w = (uint32_t)TAG_SITE_SHARED;
+      } else {
+        ctr.w = (uint32_t)TAG_SITE_CHAIN;
+      }
+      const uint32_t r_s = sel4(philox4x32_10(ctr, a.k0, a.k1), comp);
+      const int site = (int)__umulhi(r_s, (uint32_t)N);
+      // natural-log uniform
+      const R logu = SMath<R>::log2u(r_u) * (R)LN2;
+
+      const uint32_t word = sg[site >> 5];
+      const R xold = ((word >> (site & 31)) & 1u) ? s1 : s0;
+      const R d = ssum - R(2) * xold;
+      R pr[KMAX], pi[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int j = lane + 32 * k;
+        pr[k] = thr[k];
+        pi[k] = thi[k];
+        if (k < K && j < M) {
+          pr[k] = fma(d, net.W[2 * ((int64_t)site * M + j)], thr[k]);
+          pi[k] = fma(d, net.W[2 * ((int64_t)site * M + j) + 1], thi[k]);
+        }
+      }
+      cx<R> axn = ax;
+      if (net.a) axn = axn + d * mk<R>(net.a[2 * site], net.a[2 * site + 1]);
+      __syncwarp();
+      if (lane == 0) sg[site >> 5] = word ^ (1u << (site & 31));  // tentatively flip
+      __syncwarp();
+      const R logpn = R(2) * composite_logamp<R, KMAX>(net, op, sg, pr, pi, axn, K, s0, s1).re;
+      const bool acc = logu < (logpn - logp);
+      if (acc) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          thr[k] = pr[k];
+          thi[k] = pi[k];
+        }
+        ax = axn;
+        logp = logpn;
+        if (lane == 0) ++n_acc;
+      } else {
+        __syncwarp();
+        if (lane == 0) sg[site >> 5] = word;  // undo
+      }
+      __syncwarp();
+    }
+    if (sweep >= a.n_discard) {
+      const int ts = sweep - a.n_discard;
+      for (int w = lane; w < W32; w += 32) a.samples[(ch * a.chain_length + ts) * W32 + w] = sg[w];
+    }
+  }
+  for (int w = lane; w < W32; w += 32) a.chain_state[ch * W32 + w] = sg[w];
+  if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+}
+
+// ------------------------------------------------------------------ dispatch
+template <typename R, int L, int KMAX, int C>
+static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
+  constexpr int NCH = (32 / L) * C;
+  const int W32 = (net->n_visible + 31) >> 5;
+  const int64_t warps = (a.n_chains + NCH - 1) / NCH;
+  const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
+  const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    int rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, KMAX, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem);
+    if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
+  }
+  sample_plain_kernel<R, L, KMAX, C><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(make_netdev<R>(net), a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+template <typename R, int L>
+static int dispatch_plain_k(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int K, cudaStream_t st) {
+  constexpr bool dbl = sizeof(R) == 8;
+  if (K <= 4) return launch_plain<R, L, 4, dbl ? 2 : 4>(h, net, a, st);
+  if (K <= 8) return launch_plain<R, L, 8, dbl ? 2 : 4>(h, net, a, st);
+  if (K <= 16) return launch_plain<R, L, 16, dbl ? 1 : 2>(h, net, a, st);
+  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden too large for the register-resident sampler");
+}
+
+template <typename R>
+static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
+  const int M = net->n_hidden;
+  // choose the lane-group width with the least padded work; ties -> wider group
+  int bestL = 0, bestWork = 1 << 30;
+  const int Ls[4] = {32, 16, 8, 4};
+  for (int q = 0; q < 4; ++q) {
+    const int L = Ls[q], K = (M + L - 1) / L;
+    if (K > 16) continue;
+    if (L * K < bestWork) {
+      bestWork = L * K;
+      bestL = L;
+    }
+  }
+  if (bestL == 0) {
+    if (M <= 1024) return launch_plain<R, 32, 32, 1>(h, net, a, st);
+    NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden = %d > 1024 is not supported by the sampler", M);
+  }
+  const int K = (M + bestL - 1) / bestL;
+  switch (bestL) {
+    case 32: return dispatch_plain_k<R, 32>(h, net, a, K, st);
+    case 16: return dispatch_plain_k<R, 16>(h, net, a, K, st);
+    case 8: return dispatch_plain_k<R, 8>(h, net, a, K, st);
+    default: return dispatch_plain_k<R, 4>(h, net, a, K, st);
+  }
+}
+
+template <typename R, int KMAX>
+static int launch_composite(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
+  const int W32 = (net->n_visible + 31) >> 5;
+  const int64_t blocks = (a.n_chains + SAMP_WARPS - 1) / SAMP_WARPS;
+  const size_t smem = (size_t)SAMP_WARPS * W32 * sizeof(uint32_t);
+  sample_composite_kernel<R, KMAX><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(make_netdev<R>(net), a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+template <typename R>
+static int dispatch_composite(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
+  const int K = (net->n_hidden + 31) / 32;
+  if (K <= 4) return launch_composite<R, 4>(h, net, a, st);
+  if (K <= 8) return launch_composite<R, 8>(h, net, a, st);
+  if (K <= 16) return launch_composite<R, 16>(h, net, a, st);
+  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden = %d > 512 is not supported by the composite-target sampler",
+            net->n_hidden);
+}
+
+}  // namespace nkfb
+
+using namespace nkfb;
+
+extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
+                           const nkfb_sample_cfg_t *cfg, uint32_t *chain_state, uint32_t *samples,
+                           unsigned long long *n_accepted, void *stream) {
+  if (!h) return NKFB_ERR_INVALID;
+  if (!net || !net->kernel || !cfg) NKFB_FAIL(h, NKFB_ERR_INVALID, "null argument");
+  if (net->dtype != NKFB_F32 && net->dtype != NKFB_F64) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM dtype");
+  if (net->n_visible < 1 || net->n_hidden < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM shape");
+  if (cfg->n_chains <= 0) return NKFB_OK;
+  if (!chain_state || (!samples && cfg->chain_length > 0)) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
+  if (cfg->chain_length < 0 || cfg->n_discard < 0 || cfg->sweep_size < 1)
+    NKFB_FAIL(h, NKFB_ERR_INVALID, "bad chain_length / n_discard / sweep_size");
+  if (cfg->chain_offset + (uint64_t)cfg->n_chains > 0xffffffffull)
+    NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "more than 2^32 chains");
+  if (op && op->kind == NKFB_OP_GATE && (op->idx < 0 || op->idx >= net->n_visible))
+    NKFB_FAIL(h, NKFB_ERR_INVALID, "gate site outside the lattice");
+  SampArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_chains = cfg->n_chains;
+  a.chain_length = cfg->chain_length;
+  a.n_discard = cfg->n_discard;
+  a.sweep_size = cfg->sweep_size;
+  a.site_mode = cfg->site_mode;
+  a.init_random = cfg->init_random;
+  a.k0 = (uint32_t)cfg->seed;
+  a.k1 = (uint32_t)(cfg->seed >> 32);
+  a.chain_offset = cfg->chain_offset;
+  a.step_offset = cfg->step_offset;
+  a.s0 = cfg->local_states[0];
+  a.s1 = cfg->local_states[1];
+  a.chain_state = chain_state;
+  a.samples = samples;
+  a.n_accepted = n_accepted;
+  a.op = make_opdev(op);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool composite = op && op->kind != NKFB_OP_NONE;
+  if (net->dtype == NKFB_F32)
+    return composite ? dispatch_composite<float>(h, net, a, st) : dispatch_plain<float>(h, net, a, st);
+  return composite ? dispatch_composite<double>(h, net, a, st) : dispatch_plain<double>(h, net, a, st);
+}

@@ -1,0 +1,198 @@
+"""GPU parity tests (call through the C ABI).  Tolerances (BASELINE.json north_star):
+connected elements bit-exact; log psi / estimator / gradient on a fixed batch within
+1e-10 relative (fp64 kernels) and 1e-5 relative (fp32 kernels) of the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import operators as oops
+from oracle.rbm import RBMParams, rbm_logpsi, logpsi_U
+from oracle.infidelity import infidelity_and_grad, mode_slots
+from tests._helpers import to_rbmspec, to_opspec, pack_np, packed_to_torch, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.complex128: 1e-10, torch.complex64: 1e-5}
+LS = (-1.0, 1.0)
+
+
+@pytest.fixture(scope="module")
+def h():
+    from netket_fidelity_b200._native import get_handle
+    return get_handle(0)
+
+
+def _rand_states(rng, B, N, ls=LS):
+    return rng.choice(np.asarray(ls), size=(B, N))
+
+
+def _net(N, M, seed, std):
+    p = RBMParams.random(N, -(-M // N), seed, std=std)
+    return RBMParams(p.kernel[:, :M].copy(), p.bias[:M].copy(), p.visible_bias)
+
+
+# ------------------------------------------------------------------ pack / conn
+@pytest.mark.parametrize("N", [1, 3, 31, 32, 33, 64, 100])
+@pytest.mark.parametrize("ls", [(-1.0, 1.0), (0.0, 1.0)])
+def test_pack_unpack_roundtrip(h, N, ls):
+    rng = np.random.default_rng(N)
+    x = _rand_states(rng, 257, N, ls)
+    for dt in (torch.float64, torch.float32):
+        xt = torch.tensor(x, dtype=dt, device="cuda")
+        p = h.pack(xt, ls)
+        np.testing.assert_array_equal(p.cpu().numpy().view(np.uint32), pack_np(x, ls[1]))
+        back = h.unpack(p, N, ls, dt)
+        assert torch.equal(back, xt)
+
+
+def test_pack_empty(h):
+    x = torch.empty((0, 5), dtype=torch.float64, device="cuda")
+    assert h.pack(x, LS).shape == (0, 1)
+
+
+def test_conn_golden_vectors(h):
+    """test/test_operator.py:66-96 literals, through the CUDA kernel."""
+    from tests.test_oracle_gates import CONNS_QUBIT, CONNS_SPIN, MELS_RX, MELS_RY, MELS_H
+    from oracle.exact import all_states
+    for ls, conns in (((0.0, 1.0), CONNS_QUBIT), ((-1.0, 1.0), CONNS_SPIN)):
+        sig = all_states(3, ls)[[2, 7]]
+        x = torch.tensor(sig, device="cuda")
+        for op, mels in ((oops.Rx(3, 0, np.pi / 2, ls), MELS_RX), (oops.Ry(3, 0, np.pi / 2, ls), MELS_RY),
+                         (oops.Hadamard(3, 0, ls), MELS_H)):
+            xp, m = h.conn(to_opspec(op), x, ls)
+            np.testing.assert_array_equal(xp.cpu().numpy(), conns)
+            np.testing.assert_allclose(m.cpu().numpy(), mels, rtol=1e-7)
+
+
+@pytest.mark.parametrize("N", [3, 20, 40, 100])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_conn_bit_exact_vs_oracle(h, N, dt):
+    rng = np.random.default_rng(7 + N)
+    x = _rand_states(rng, 513, N)
+    xt = torch.tensor(x, dtype=dt, device="cuda")
+    edges = oops.chain_edges(N)
+    ops = [oops.Rx(N, N // 2, 0.3), oops.Ry(N, 0, 1.1), oops.Hadamard(N, N - 1),
+           oops.Ising(N, edges, 0.7, 1.3), oops.IsingPropagator(N, edges, 1.0, 1.0, 0.01)]
+    for op in ops:
+        xp_ref, mels_ref = op.get_conn_padded(x)
+        xp, mels = h.conn(to_opspec(op), xt, LS)
+        assert xp.dtype == dt
+        np.testing.assert_array_equal(xp.cpu().numpy().astype(np.float64), xp_ref)        # bit-exact
+        np.testing.assert_array_equal(mels.cpu().numpy(), mels_ref.astype(np.complex128))  # bit-exact
+
+
+# ------------------------------------------------------------------ log psi
+SHAPES = [(3, 3), (4, 4), (20, 40), (33, 70), (40, 80), (100, 400)]
+
+
+def _cmp_logamp(got, ref, tol):
+    """complex log-amplitudes: real parts relative to their scale, phases mod 2 pi."""
+    got, ref = np.asarray(got).astype(np.complex128), np.asarray(ref)
+    scale = max(1.0, np.max(np.abs(ref.real)))
+    assert np.max(np.abs(got.real - ref.real)) <= tol * scale
+    dphi = np.angle(np.exp(1j * (got.imag - ref.imag)))
+    assert np.max(np.abs(dphi)) <= tol * max(1.0, np.max(np.abs(ref.imag)))
+
+
+@pytest.mark.parametrize("N,M", SHAPES)
+@pytest.mark.parametrize("cd", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("std", [0.01, 0.1])
+def test_logpsi_plain(h, N, M, cd, std):
+    rng = np.random.default_rng(N * 1000 + M)
+    p = _net(N, M, 1234, std)
+    x = _rand_states(rng, 300, N)
+    ref = rbm_logpsi(p, x)
+    got = h.logpsi(to_rbmspec(p, cd), packed_to_torch(pack_np(x)), LS).cpu().numpy()
+    _cmp_logamp(got, ref, TOL[cd])
+
+
+@pytest.mark.parametrize("N,M", [(3, 3), (20, 40), (40, 80), (100, 400)])
+@pytest.mark.parametrize("cd", [torch.complex128, torch.complex64])
+def test_logpsi_U(h, N, M, cd):
+    rng = np.random.default_rng(N + M)
+    p = _net(N, M, 77, 0.1)
+    x = _rand_states(rng, 200, N)
+    edges = oops.chain_edges(N)
+    for op in (oops.Rx(N, 1, 0.4), oops.Ry(N, N - 1, 0.9), oops.Hadamard(N, 0),
+               oops.IsingPropagator(N, edges, 1.0, 1.0, 0.01), oops.Ising(N, edges, 0.5, 1.0)):
+        ref = logpsi_U(p, op, x)
+        got = h.logpsi(to_rbmspec(p, cd), packed_to_torch(pack_np(x)), LS, to_opspec(op)).cpu().numpy()
+        _cmp_logamp(got, ref, TOL[cd] * (10 if isinstance(op, oops.IsingLike) else 1))
+
+
+def test_logpsi_no_biases_and_qubit_states(h):
+    rng = np.random.default_rng(3)
+    p = RBMParams.random(6, 2, 5, std=0.2, use_hidden_bias=False, use_visible_bias=False)
+    ls = (0.0, 1.0)
+    x = _rand_states(rng, 100, 6, ls)
+    got = h.logpsi(to_rbmspec(p, torch.complex128), packed_to_torch(pack_np(x, 1.0)), ls).cpu().numpy()
+    _cmp_logamp(got, rbm_logpsi(p, x), 1e-10)
+
+
+# ------------------------------------------------------------------ estimator + gradient
+def _modes(N):
+    e = oops.chain_edges(N)
+    return [
+        ("standard", None, None),
+        ("upsi", oops.Rx(N, N // 2, 0.37), oops.Rx(N, N // 2, -0.37)),
+        ("upsi", oops.Ry(N, 0, 0.51), oops.Ry(N, 0, -0.51)),
+        ("upsi", oops.Hadamard(N, N - 1), oops.Hadamard(N, N - 1)),
+        ("standard_Uphi", oops.Rx(N, 1, 0.2), None),
+        ("standard_Uphi", oops.IsingPropagator(N, e, 1.0, 1.0, 0.01), None),
+    ]
+
+
+@pytest.mark.parametrize("N,M,S", [(3, 3, 100), (4, 4, 112), (20, 40, 1000), (33, 70, 300), (100, 400, 4096)])
+@pytest.mark.parametrize("cd", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("cv", [None, -0.5])
+def test_infidelity_fwd_and_grad_fixed_batch(h, N, M, S, cd, cv):
+    rng = np.random.default_rng(42)
+    psi, phi = _net(N, M, 1234, 0.05), _net(N, M, 5678, 0.05)
+    sigma = _rand_states(rng, S, N)
+    eta = _rand_states(rng, S, N)
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    tol = TOL[cd]
+    for mode, U, Ud in _modes(N):
+        if N == 100 and isinstance(U, oops.IsingLike):
+            continue  # keeps the CPU oracle within seconds; Ising at N=40 is covered above
+        U1, U2, U4 = mode_slots(mode, U, Ud)
+        ref = infidelity_and_grad(psi, phi, sigma, eta, cv, U1, U2, U4)
+        a, b = to_rbmspec(psi, cd), to_rbmspec(phi, cd)
+        lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, cv, to_opspec(U1), to_opspec(U2), to_opspec(U4))
+        assert rel_err(L.cpu().numpy(), ref["L"]) <= tol * 10, (mode, U)
+        s = sums.cpu().numpy()
+        assert s[4] == S
+        assert abs(s[0] / S - ref["F"]) <= tol * max(1.0, abs(ref["F"]))
+        gacc = h.infidelity_grad(a, sp, ep, LS, cv, lv, rho1, sums, to_opspec(U2))
+        g = h.grad_finalize(gacc, sums, a.n_params, cd).cpu().numpy()
+        gref = ref["grad"].ravel()
+        assert rel_err(g, gref) <= tol * 20, (mode, U, rel_err(g, gref))
+
+
+def test_gradient_without_visible_bias(h):
+    rng = np.random.default_rng(1)
+    N, S = 4, 112
+    psi = RBMParams.random(N, 1, 1, std=0.2, use_visible_bias=False)
+    phi = RBMParams.random(N, 1, 2, std=0.2, use_visible_bias=False)
+    sigma, eta = _rand_states(rng, S, N), _rand_states(rng, S, N)
+    U = oops.Hadamard(N, 0)
+    ref = infidelity_and_grad(psi, phi, sigma, eta, -0.5, U, U, None)
+    a, b = to_rbmspec(psi, torch.complex128), to_rbmspec(phi, torch.complex128)
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, -0.5, to_opspec(U), to_opspec(U), None)
+    gacc = h.infidelity_grad(a, sp, ep, LS, -0.5, lv, rho1, sums, to_opspec(U))
+    g = h.grad_finalize(gacc, sums, a.n_params, torch.complex128).cpu().numpy()
+    M = psi.M
+    gref = ref["grad"]
+    np.testing.assert_allclose(g[:M], gref.bias, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(g[M:M + N * M].reshape(N, M), gref.kernel, rtol=1e-9, atol=1e-13)
+    assert np.all(g[M + N * M:] == 0)     # no visible bias: untouched accumulators
+
+
+def test_errors_are_reported_not_swallowed(h):
+    from netket_fidelity_b200._native import NkfbError, OpSpec, OP_GATE
+    p = RBMParams.random(4, 1, 1)
+    a = to_rbmspec(p, torch.complex128)
+    x = packed_to_torch(pack_np(np.ones((4, 4))))
+    with pytest.raises(NkfbError):
+        h.logpsi(a, x, LS, OpSpec(OP_GATE, 7, [[1, 0], [1, 0]]))   # site outside the lattice
