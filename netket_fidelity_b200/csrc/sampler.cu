@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
     R sumabs = R(0), prod = R(1), lg = R(0);
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      if (k < K && l + L * k < M) SMath<R>::unit(thr[c][k], thi[c][k], sumabs, prod);
+      if (k < K) SMath<R>::unit(thr[c][k], thi[c][k], sumabs, prod);  // padded units add the same constant as in the MH loop
       if ((k & 3) == 3) lg += SMath<R>::flush(prod);
     }
     lc[c] = group_sum<L>(SMath<R>::finish(sumabs, lg));
