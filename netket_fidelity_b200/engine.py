@@ -1,0 +1,135 @@
+"""One infidelity-gradient step of p-tVMC on one GPU (or one rank of a multi-GPU job).
+
+This is the device-side pipeline that `MCState.expect_and_grad(InfidelityOperator...)`
+drives (reference call stack: driver/infidelity_optimizer.py:141-150 ->
+infidelity/overlap/expect.py:33-55 or infidelity/overlap_U/expect.py:40-67):
+
+    sample sigma ~ |psi|^2, eta ~ |Phi|^2      nkfb_sample      (x2)
+    pass A: local estimator + CV, sums         nkfb_infidelity_fwd
+    [all-reduce of 8 doubles when world_size > 1]
+    pass B: score-function gradient            nkfb_infidelity_grad
+    [all-reduce of the 2P-double accumulator when world_size > 1]
+    I_grad = -acc / n                          nkfb_grad_finalize
+
+Markov chains are sharded over ranks: rank r owns the global chains
+[r * n_chains / G, (r+1) * n_chains / G) of both families; the Philox streams are keyed
+by the GLOBAL chain id, so the samples do not depend on G.  torch.distributed is used only
+as plumbing for the two all-reduces.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _native as nv
+
+
+class StepConfig:
+    def __init__(self, n_chains, chain_length, n_discard, sweep_size=None, seed=0, local_states=(-1.0, 1.0),
+                 cv_coeff=-0.5, site_mode=0):
+        self.n_chains = int(n_chains)            # GLOBAL number of chains per family
+        self.chain_length = int(chain_length)
+        self.n_discard = int(n_discard)
+        self.sweep_size = sweep_size
+        self.seed = int(seed)
+        self.local_states = tuple(local_states)
+        self.cv_coeff = cv_coeff
+        self.site_mode = site_mode
+
+
+class InfidelityStep:
+    """Owns the per-rank buffers of one (psi, phi, U) problem and runs steps on them.
+
+    mode: "standard" (Phi = phi), "standard_Uphi" (Phi = U phi, sampled from; reference
+    InfidelityUPsi, overlap/operator.py:61-82) or "upsi" (unitary U; conns of U and U^dagger;
+    reference InfidelityOperatorUPsi, overlap_U/operator.py:12-67).
+    """
+
+    def __init__(self, N, M, cfg: StepConfig, mode="upsi", U: nv.OpSpec | None = None,
+                 U_dagger: nv.OpSpec | None = None, device=None, cdtype=torch.complex64, group=None):
+        self.h = nv.get_handle(device)
+        self.dev = self.h.device
+        self.N, self.M, self.cfg, self.mode = N, M, cfg, mode
+        self.cdtype = cdtype
+        self.group = group
+        self.world, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        if cfg.n_chains % self.world:
+            raise ValueError(f"n_chains={cfg.n_chains} must be divisible by the number of ranks {self.world}")
+        self.local_chains = cfg.n_chains // self.world
+        self.chain_offset = self.rank * self.local_chains
+        if mode == "standard":
+            self.op1 = self.op2 = self.op4 = self.op_target = None
+        elif mode == "standard_Uphi":
+            self.op1, self.op2, self.op4, self.op_target = U, None, U, U
+        elif mode == "upsi":
+            if U is None or U_dagger is None:
+                raise ValueError("mode 'upsi' needs U and U_dagger")
+            self.op1, self.op2, self.op4, self.op_target = U, U_dagger, None, None
+        else:
+            raise ValueError(mode)
+        W32 = (N + 31) // 32
+        self.W32 = W32
+        dev = self.dev
+        self.state_psi = torch.zeros((self.local_chains, W32), dtype=torch.int32, device=dev)
+        self.state_phi = torch.zeros((self.local_chains, W32), dtype=torch.int32, device=dev)
+        self.sigma = torch.empty((self.local_chains, cfg.chain_length, W32), dtype=torch.int32, device=dev)
+        self.eta = torch.empty_like(self.sigma)
+        self.S_local = self.local_chains * cfg.chain_length
+        self.S_total = cfg.n_chains * cfg.chain_length
+        P = N * M + M + N
+        self.P = P
+        # one zero-able block: [sums (8) | grad accumulators (2P)]
+        self.acc = torch.zeros((8 + 2 * P,), dtype=torch.float64, device=dev)
+        self.sums = self.acc[:8]
+        self.grad_acc = self.acc[8:]
+        self.n_accepted = torch.zeros((2,), dtype=torch.int64, device=dev)
+        self.steps_done = 0
+        self.initialised = False
+        self.sweep = cfg.sweep_size if cfg.sweep_size is not None else N
+        self.last = {}
+
+    # ------------------------------------------------------------------
+    def sample(self, psi: nv.RbmSpec, phi: nv.RbmSpec):
+        cfg = self.cfg
+        init = not self.initialised
+        step_offset = self.steps_done * (cfg.n_discard + cfg.chain_length) * self.sweep
+        # the two families use disjoint global chain ids: psi [0, n_chains), phi [n_chains, 2 n_chains)
+        self.h.sample(psi, self.state_psi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
+                      cfg.local_states, op=None, chain_offset=self.chain_offset, step_offset=step_offset,
+                      site_mode=cfg.site_mode, init_random=init, n_accepted=self.n_accepted[0:1], out=self.sigma)
+        self.h.sample(phi, self.state_phi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
+                      cfg.local_states, op=self.op_target, chain_offset=cfg.n_chains + self.chain_offset,
+                      step_offset=step_offset, site_mode=cfg.site_mode, init_random=init,
+                      n_accepted=self.n_accepted[1:2], out=self.eta)
+        self.initialised = True
+        self.steps_done += 1
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def estimate(self, psi, phi, return_grad=True):
+        """Pass A (+ pass B).  Returns (sums[8] device tensor, L (S_local,), grad (P,) complex | None)."""
+        cfg = self.cfg
+        sig = self.sigma.view(-1, self.W32)
+        eta = self.eta.view(-1, self.W32)
+        self.acc.zero_()
+        log_val, L, rho1, _ = self.h.infidelity_fwd(psi, phi, sig, eta, cfg.local_states, cfg.cv_coeff, self.op1,
+                                                    self.op2, self.op4, sums=self.sums)
+        self._allreduce(self.sums)
+        grad = None
+        if return_grad:
+            self.h.infidelity_grad(psi, sig, eta, cfg.local_states, cfg.cv_coeff, log_val, rho1, self.sums,
+                                   op2=self.op2, grad_acc=self.grad_acc)
+            self._allreduce(self.grad_acc)
+            grad = self.h.grad_finalize(self.grad_acc, self.sums, self.P, self.cdtype)
+        self.last = dict(log_val=log_val, L=L, rho1=rho1)
+        return self.sums, L, grad
+
+    def step(self, psi, phi, return_grad=True):
+        """reset + sample both families + estimator (+ gradient): the unit bench.py times."""
+        self.sample(psi, phi)
+        return self.estimate(psi, phi, return_grad)
