@@ -187,6 +187,16 @@ int nkfb_renyi2(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *samples,
                 uint32_t *scratch /* device (2*S_half, W32) */, void *scratch_logpsi /* device (4*S_half) complex */,
                 void *q, double *sums, void *stream);
 
+/* ---- optimiser update ---------------------------------------------------- */
+/* Replaces the optax update applied by NetKet's AbstractVariationalDriver.update_parameters
+ * (called from InfidelityOptimizer.run, driver/infidelity_optimizer.py:188).  kind 0: SGD,
+ * kind 1: Adam (optax.adam; |g|^2 second moment for complex leaves), step t >= 1.
+ * params/grad/m: device (P) complex of `dtype` (flat layout); v: device (P) real.
+ * real_params != 0: the imaginary part of the gradient is ignored (real-parameter model). */
+int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void *params, const void *grad,
+                          void *m, void *v, int64_t P, double lr, double b1, double b2, double eps,
+                          int64_t t, int real_params, void *stream);
+
 /* ---- MUFU / FP32 micro-benchmarks (roofline denominators) ---------------- */
 /* Runs `iters` dependent-free MUFU.EX2 (kind 0), MUFU.COS (1), MUFU.LG2 (2) or FFMA (3)
  * per thread on a full grid; returns operations/second measured with CUDA events. */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "nkfb_version", "nkfb_create", "nkfb_destroy", "nkfb_last_error", "nkfb_launch_count",
     "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
-    "nkfb_renyi2", "nkfb_microbench",
+    "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library():
         lib.nkfb_chain_stats.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp]
         lib.nkfb_renyi2.argtypes = [vp, P(RbmT), vp, i64, vp, P(dbl), vp, vp, vp, vp, vp]
         lib.nkfb_microbench.argtypes = [vp, i32, i32, P(dbl), vp]
+        lib.nkfb_optimizer_update.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, i64, i32, vp]
         for name in SYMBOLS:
             getattr(lib, name)  # AttributeError if the ABI drifted
         _lib = lib
@@ -341,6 +342,13 @@ class Handle:
                                          _ls(local_states), _ptr(scratch), _ptr(lp), _ptr(q), _ptr(sums), _stream()),
                     "nkfb_renyi2")
         return q, sums
+
+    # ---------------------------------------------------------------- optimiser
+    def optimizer_update(self, kind, params, grad, m, v, lr, b1, b2, eps, t, real_params):
+        P = params.numel()
+        self._check(self.lib.nkfb_optimizer_update(self.h, kind, real_dtype_code(params.dtype), _ptr(params),
+                                                   _ptr(grad), _ptr(m), _ptr(v), P, lr, b1, b2, eps, t,
+                                                   1 if real_params else 0, _stream()), "nkfb_optimizer_update")
 
     # ---------------------------------------------------------------- micro-benchmarks
     def microbench(self, kind, iters=4096):

@@ -336,3 +336,49 @@ extern "C" int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops
   *ops_per_second = best;
   return NKFB_OK;
 }
+
+// ------------------------------------------------------------------ optimiser update (driver loop)
+namespace nkfb {
+// kind 0: SGD  p -= lr g.   kind 1: Adam (optax.adam semantics; second moment uses |g|^2 for
+// complex leaves): m = b1 m + (1-b1) g; v = b2 v + (1-b2)|g|^2; p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
+template <typename R>
+__global__ void optimizer_kernel(int kind, R *p, const R *g, R *m, R *v, int64_t P, double lr, double b1, double b2,
+                                 double eps, double c1, double c2, int real_params) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    double gr = (double)g[2 * i], gi = real_params ? 0.0 : (double)g[2 * i + 1];
+    if (kind == 0) {
+      p[2 * i] = (R)((double)p[2 * i] - lr * gr);
+      p[2 * i + 1] = (R)((double)p[2 * i + 1] - lr * gi);
+    } else {
+      double mr = b1 * (double)m[2 * i] + (1.0 - b1) * gr, mi = b1 * (double)m[2 * i + 1] + (1.0 - b1) * gi;
+      double vv = b2 * (double)v[i] + (1.0 - b2) * (gr * gr + gi * gi);
+      m[2 * i] = (R)mr;
+      m[2 * i + 1] = (R)mi;
+      v[i] = (R)vv;
+      double den = sqrt(vv / c2) + eps;
+      p[2 * i] = (R)((double)p[2 * i] - lr * (mr / c1) / den);
+      p[2 * i + 1] = (R)((double)p[2 * i + 1] - lr * (mi / c1) / den);
+    }
+  }
+}
+}  // namespace nkfb
+
+extern "C" int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void *params, const void *grad, void *m,
+                                     void *v, int64_t P, double lr, double b1, double b2, double eps, int64_t t,
+                                     int real_params, void *stream) {
+  if (!h) return NKFB_ERR_INVALID;
+  if (!params || !grad || P <= 0 || (kind == 1 && (!m || !v)) || t < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad optimizer arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double c1 = 1.0 - pow(b1, (double)t), c2 = 1.0 - pow(b2, (double)t);
+  int grid = grid_for(P, h->sm_count);
+  if (dtype == NKFB_F32)
+    optimizer_kernel<float><<<grid, 256, 0, st>>>(kind, (float *)params, (const float *)grad, (float *)m, (float *)v, P,
+                                                  lr, b1, b2, eps, c1, c2, real_params);
+  else if (dtype == NKFB_F64)
+    optimizer_kernel<double><<<grid, 256, 0, st>>>(kind, (double *)params, (const double *)grad, (double *)m,
+                                                   (double *)v, P, lr, b1, b2, eps, c1, c2, real_params);
+  else
+    NKFB_FAIL(h, NKFB_ERR_INVALID, "bad dtype");
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}

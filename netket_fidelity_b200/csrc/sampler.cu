@@ -13,285 +13,9 @@
 // Composite target (|sum_c mel_c phi(x'_c)|^2, c over the connected elements of a gate or
 // of an Ising-type operator): one warp per chain, complex log cosh for every connected
 // configuration of the proposal.
-#include <cstdio>
-#include <cstring>
-
-#include "tile.cuh"
+#include "sampler_common.cuh"
 
 namespace nkfb {
-
-enum { TAG_UNIFORM = 0, TAG_SITE_CHAIN = 1, TAG_SITE_SHARED = 2, TAG_INIT = 3 };
-
-struct SampArgs {
-  int64_t n_chains;
-  int chain_length, n_discard, sweep_size, site_mode, init_random;
-  uint32_t k0, k1;
-  uint64_t chain_offset, step_offset;
-  double s0, s1;
-  uint32_t *chain_state, *samples;
-  unsigned long long *n_accepted;
-  OpDev op;
-};
-
-template <typename R>
-struct SMath;
-template <>
-struct SMath<float> {
-  // returns the log2-domain pieces: adds |x| to sumabs, multiplies prod by (1 + t^2 + 2 t cos 2y)
-  static __device__ __forceinline__ void unit(float x, float y, float &sumabs, float &prod) {
-    const float ax = fabsf(x);
-    const float t = mufu_ex2(ax * (float)(-2.0 * LOG2E));
-    const float c = mufu_cos(2.0f * y);
-    prod *= fmaf(t, fmaf(2.0f, c, t), 1.0f);
-    sumabs += ax;
-  }
-  static __device__ __forceinline__ float flush(float &prod) {
-    float r = mufu_lg2(prod);
-    prod = 1.0f;
-    return r;
-  }
-  static __device__ __forceinline__ float finish(float sumabs, float lg) {
-    return fmaf(sumabs, (float)LOG2E, 0.5f * lg);
-  }
-  static __device__ __forceinline__ float log2u(uint32_t r) {
-    return mufu_lg2(((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f));
-  }
-};
-template <>
-struct SMath<double> {
-  static __device__ __forceinline__ void unit(double x, double y, double &sumabs, double &prod) {
-    const double ax = fabs(x);
-    const double t = exp(-2.0 * ax);
-    const double c = cos(2.0 * y);
-    prod *= fma(t, fma(2.0, c, t), 1.0);
-    sumabs += ax;
-  }
-  static __device__ __forceinline__ double flush(double &prod) {
-    double r = log2(prod);
-    prod = 1.0;
-    return r;
-  }
-  static __device__ __forceinline__ double finish(double sumabs, double lg) { return fma(sumabs, LOG2E, 0.5 * lg); }
-  static __device__ __forceinline__ double log2u(uint32_t r) { return log2(((double)r + 0.5) * (1.0 / 4294967296.0)); }
-};
-
-template <int L, typename T>
-__device__ __forceinline__ T group_sum(T v) {
-#pragma unroll
-  for (int m = L / 2; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  return v;
-}
-
-__device__ __forceinline__ uint32_t sel4(const u32x4 &v, int c) {
-  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
-}
-
-constexpr int SAMP_WARPS = 4;
-
-// =====================================================================================
-template <typename R, int L, int KMAX, int C>
-__global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R> net, SampArgs a) {
-  constexpr int G = 32 / L;      // chain groups per warp
-  constexpr int NCH = G * C;     // chains per warp
-  constexpr int BLK = 32 / NCH;  // Philox blocks per chain per batch
-  constexpr int SB = 4 * BLK;    // MH steps per RNG batch
-  extern __shared__ uint32_t sig_all[];
-  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / L, l = lane % L;
-  const int K = (M + L - 1) / L;
-  uint32_t *sig = sig_all + (size_t)warp * NCH * W32;  // [NCH][W32]
-  const int64_t warp_global = (int64_t)blockIdx.x * SAMP_WARPS + warp;
-  const int64_t chain0 = warp_global * NCH;  // first local chain of this warp
-  if (chain0 >= a.n_chains) return;
-  const R s0 = (R)a.s0, s1 = (R)a.s1, ssum = s0 + s1;
-
-  // ---- load / initialise configurations
-  for (int idx = lane; idx < NCH * W32; idx += 32) {
-    const int slot = idx / W32, w = idx - slot * W32;
-    const int64_t ch = chain0 + slot;
-    uint32_t v = 0;
-    if (ch < a.n_chains) {
-      if (a.init_random) {
-        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + ch), (uint32_t)TAG_INIT};
-        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
-      } else {
-        v = a.chain_state[ch * W32 + w];
-      }
-      const int nb = N - 32 * w;
-      if (nb < 32) v &= (1u << nb) - 1u;
-    }
-    sig[idx] = v;
-  }
-  __syncwarp();
-
-  // ---- theta from scratch
-  R thr[C][KMAX], thi[C][KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const int j = l + L * k;
-    R br = R(0), bi = R(0);
-    if (k < K && j < M && net.b) {
-      br = net.b[2 * j];
-      bi = net.b[2 * j + 1];
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      thr[c][k] = br;
-      thi[c][k] = bi;
-    }
-  }
-  for (int i = 0; i < N; ++i) {
-    R xv[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) xv[c] = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int j = l + L * k;
-      if (k < K && j < M) {
-        const R wr = net.W[2 * ((int64_t)i * M + j)], wi = net.W[2 * ((int64_t)i * M + j) + 1];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          thr[c][k] = fma(xv[c], wr, thr[c][k]);
-          thi[c][k] = fma(xv[c], wi, thi[c][k]);
-        }
-      }
-    }
-  }
-  R lc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    R sumabs = R(0), prod = R(1), lg = R(0);
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) SMath<R>::unit(thr[c][k], thi[c][k], sumabs, prod);  // padded units add the same constant as in the MH loop
-      if ((k & 3) == 3) lg += SMath<R>::flush(prod);
-    }
-    lc[c] = group_sum<L>(SMath<R>::finish(sumabs, lg));
-  }
-
-  unsigned n_acc = 0;
-  const int total_sweeps = a.n_discard + a.chain_length;
-  uint64_t step = a.step_offset;  // global MH step index (multiple of SB is NOT required)
-  u32x4 ru = {0, 0, 0, 0}, rs = {0, 0, 0, 0};
-  R lu[4] = {R(0), R(0), R(0), R(0)};
-  uint64_t batch_base = ~0ull;  // first step covered by the current RNG batch
-
-  for (int sweep = 0; sweep < total_sweeps; ++sweep) {
-    for (int t = 0; t < a.sweep_size; ++t, ++step) {
-      // ---- refill the RNG batch: lane r serves chain slot r % NCH, Philox block r / NCH
-      const uint64_t bb = step - (step % SB);
-      if (bb != batch_base) {
-        batch_base = bb;
-        const uint64_t blk = bb / 4 + (uint64_t)(lane / NCH);
-        const uint32_t chid = (uint32_t)(a.chain_offset + chain0 + (lane % NCH));
-        u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
-        ru = philox4x32_10(ctr, a.k0, a.k1);
-        lu[0] = SMath<R>::log2u(ru.x);
-        lu[1] = SMath<R>::log2u(ru.y);
-        lu[2] = SMath<R>::log2u(ru.z);
-        lu[3] = SMath<R>::log2u(ru.w);
-        if (a.site_mode == 0) {
-          const uint64_t sblk = bb / 4 + (uint64_t)(lane % BLK);
-          u32x4 c2 = {(uint32_t)sblk, (uint32_t)(sblk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
-          rs = philox4x32_10(c2, a.k0, a.k1);
-        } else {
-          ctr.w = (uint32_t)TAG_SITE_CHAIN;
-          rs = philox4x32_10(ctr, a.k0, a.k1);
-        }
-      }
-      const int tb = (int)(step - batch_base);  // 0 .. SB-1
-      const int bi = tb >> 2, comp = tb & 3;
-      const uint32_t my_rs = sel4(rs, comp);
-      const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
-
-      int site_shared = 0;
-      R wr[KMAX], wi[KMAX];
-      R ar_shared = R(0);
-      if (a.site_mode == 0) {
-        site_shared = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int j = l + L * k;
-          wr[k] = R(0);
-          wi[k] = R(0);
-          if (k < K && j < M) {
-            wr[k] = net.W[2 * ((int64_t)site_shared * M + j)];
-            wi[k] = net.W[2 * ((int64_t)site_shared * M + j) + 1];
-          }
-        }
-        if (net.a) ar_shared = net.a[2 * site_shared];
-      }
-
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const int slot = g * C + c;
-        const int src = slot + NCH * bi;
-        const R logu = __shfl_sync(0xffffffffu, my_lu, src);
-        int site = site_shared;
-        R ar = ar_shared;
-        if (a.site_mode != 0) {
-          site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            const int j = l + L * k;
-            wr[k] = R(0);
-            wi[k] = R(0);
-            if (k < K && j < M) {
-              wr[k] = net.W[2 * ((int64_t)site * M + j)];
-              wi[k] = net.W[2 * ((int64_t)site * M + j) + 1];
-            }
-          }
-          ar = net.a ? net.a[2 * site] : R(0);
-        }
-        const uint32_t word = sig[slot * W32 + (site >> 5)];
-        const R xold = ((word >> (site & 31)) & 1u) ? s1 : s0;
-        const R d = ssum - R(2) * xold;  // x_new - x_old
-        R sumabs = R(0), prod = R(1), lg = R(0);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (k < K) SMath<R>::unit(fma(d, wr[k], thr[c][k]), fma(d, wi[k], thi[c][k]), sumabs, prod);
-          if ((k & 3) == 3) lg += SMath<R>::flush(prod);
-        }
-        const R lcn = group_sum<L>(SMath<R>::finish(sumabs, lg));
-        // log2 of the acceptance ratio |psi(x')|^2 / |psi(x)|^2
-        const R dl = R(2) * (lcn - lc[c]) + R(2.0 * LOG2E) * d * ar;
-        const bool acc = (logu < dl) && (chain0 + slot < a.n_chains);
-        const R de = acc ? d : R(0);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (k < K) {
-            thr[c][k] = fma(de, wr[k], thr[c][k]);
-            thi[c][k] = fma(de, wi[k], thi[c][k]);
-          }
-        }
-        lc[c] = acc ? lcn : lc[c];
-        if (acc && l == 0) {
-          sig[slot * W32 + (site >> 5)] = word ^ (1u << (site & 31));
-          ++n_acc;
-        }
-      }
-      __syncwarp();
-    }
-    if (sweep >= a.n_discard) {
-      const int ts = sweep - a.n_discard;
-      for (int idx = lane; idx < NCH * W32; idx += 32) {
-        const int slot = idx / W32, w = idx - slot * W32;
-        const int64_t ch = chain0 + slot;
-        if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w] = sig[idx];
-      }
-    }
-  }
-  for (int idx = lane; idx < NCH * W32; idx += 32) {
-    const int slot = idx / W32, w = idx - slot * W32;
-    const int64_t ch = chain0 + slot;
-    if (ch < a.n_chains) a.chain_state[ch * W32 + w] = sig[idx];
-  }
-  if (a.n_accepted) {
-    n_acc = warp_sum(n_acc);
-    if (lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
-  }
-}
 
 // =====================================================================================
 // Composite target: log Phi(x) = log sum_c mel_c(x) phi(x'_c).  One warp per chain.
@@ -502,36 +226,19 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_composite_kernel(NetDe
 }
 
 // ------------------------------------------------------------------ dispatch
-template <typename R, int L, int KMAX, int C>
-static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
-  constexpr int NCH = (32 / L) * C;
-  const int W32 = (net->n_visible + 31) >> 5;
-  const int64_t warps = (a.n_chains + NCH - 1) / NCH;
-  const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
-  const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
-  if (smem > 48 * 1024) {
-    int rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, KMAX, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem);
-    if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
-  }
-  sample_plain_kernel<R, L, KMAX, C><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(make_netdev<R>(net), a);
-  NKFB_LAUNCHED(h);
-  return NKFB_OK;
-}
+// plain-target kernels are instantiated per (real type, lane-group width) in sampler_inst.cu
+int dispatch_plain_f32_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f32_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f32_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f32_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f64_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f64_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f64_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
 
-template <typename R, int L>
-static int dispatch_plain_k(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int K, cudaStream_t st) {
-  constexpr bool dbl = sizeof(R) == 8;
-  if (K <= 4) return launch_plain<R, L, 4, dbl ? 2 : 4>(h, net, a, st);
-  if (K <= 8) return launch_plain<R, L, 8, dbl ? 2 : 4>(h, net, a, st);
-  if (K <= 16) return launch_plain<R, L, 16, dbl ? 1 : 2>(h, net, a, st);
-  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden too large for the register-resident sampler");
-}
-
-template <typename R>
+// lane-group width with the least padded work (ties -> wider group); K = ceil(M / L) <= 16 (32 for L = 32)
 static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
   const int M = net->n_hidden;
-  // choose the lane-group width with the least padded work; ties -> wider group
   int bestL = 0, bestWork = 1 << 30;
   const int Ls[4] = {32, 16, 8, 4};
   for (int q = 0; q < 4; ++q) {
@@ -543,15 +250,16 @@ static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs
     }
   }
   if (bestL == 0) {
-    if (M <= 1024) return launch_plain<R, 32, 32, 1>(h, net, a, st);
-    NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden = %d > 1024 is not supported by the sampler", M);
+    if (M > 1024) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "n_hidden = %d > 1024 is not supported by the sampler", M);
+    bestL = 32;
   }
   const int K = (M + bestL - 1) / bestL;
+  const bool f32 = net->dtype == NKFB_F32;
   switch (bestL) {
-    case 32: return dispatch_plain_k<R, 32>(h, net, a, K, st);
-    case 16: return dispatch_plain_k<R, 16>(h, net, a, K, st);
-    case 8: return dispatch_plain_k<R, 8>(h, net, a, K, st);
-    default: return dispatch_plain_k<R, 4>(h, net, a, K, st);
+    case 32: return f32 ? dispatch_plain_f32_L32(h, net, a, K, st) : dispatch_plain_f64_L32(h, net, a, K, st);
+    case 16: return f32 ? dispatch_plain_f32_L16(h, net, a, K, st) : dispatch_plain_f64_L16(h, net, a, K, st);
+    case 8: return f32 ? dispatch_plain_f32_L8(h, net, a, K, st) : dispatch_plain_f64_L8(h, net, a, K, st);
+    default: return f32 ? dispatch_plain_f32_L4(h, net, a, K, st) : dispatch_plain_f64_L4(h, net, a, K, st);
   }
 }
 
@@ -614,7 +322,8 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   a.op = make_opdev(op);
   cudaStream_t st = (cudaStream_t)stream;
   const bool composite = op && op->kind != NKFB_OP_NONE;
-  if (net->dtype == NKFB_F32)
-    return composite ? dispatch_composite<float>(h, net, a, st) : dispatch_plain<float>(h, net, a, st);
-  return composite ? dispatch_composite<double>(h, net, a, st) : dispatch_plain<double>(h, net, a, st);
+  if ((uint64_t)(cfg->n_discard + (int64_t)cfg->chain_length) * (uint64_t)cfg->sweep_size >= (1ull << 31))
+    NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "more than 2^31 Metropolis steps in one call");
+  if (!composite) return dispatch_plain(h, net, a, st);
+  return net->dtype == NKFB_F32 ? dispatch_composite<float>(h, net, a, st) : dispatch_composite<double>(h, net, a, st);
 }
