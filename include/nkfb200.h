@@ -93,6 +93,9 @@ typedef struct {
   double local_states[2];
   int32_t init_random;   /* !=0: ignore chain_state on input, start from Philox-random configurations */
   int32_t reserved;
+  void *workspace;         /* device scratch of >= nkfb_sample_workspace_bytes() bytes, or NULL to use the
+                              handle's own buffer (then calls on different streams must not overlap) */
+  uint64_t workspace_bytes;
 } nkfb_sample_cfg_t;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -132,6 +135,7 @@ int nkfb_logpsi(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
  * driver/infidelity_optimizer.py:142-143).  Target density |sum_c mel_c psi(x'_c)|^2.
  * chain_state: device (n_chains, W32) in/out.  samples: device
  * (n_chains, chain_length, W32).  n_accepted: device uint64[1] (accumulated) or NULL. */
+size_t nkfb_sample_workspace_bytes(int n_visible, int n_hidden, int dtype);
 int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
                 const nkfb_sample_cfg_t *cfg, uint32_t *chain_state, uint32_t *samples,
                 unsigned long long *n_accepted, void *stream);

@@ -20,7 +20,7 @@ OP_NONE, OP_GATE, OP_ISING = 0, 1, 2
 
 SYMBOLS = [
     "nkfb_version", "nkfb_create", "nkfb_destroy", "nkfb_last_error", "nkfb_launch_count",
-    "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample",
+    "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample", "nkfb_sample_workspace_bytes",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
     "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update",
 ]
@@ -46,7 +46,8 @@ class SampleCfgT(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("chain_length", C.c_int32), ("n_discard", C.c_int32),
                 ("sweep_size", C.c_int32), ("site_mode", C.c_int32), ("seed", C.c_uint64),
                 ("chain_offset", C.c_uint64), ("step_offset", C.c_uint64),
-                ("local_states", C.c_double * 2), ("init_random", C.c_int32), ("reserved", C.c_int32)]
+                ("local_states", C.c_double * 2), ("init_random", C.c_int32), ("reserved", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -78,6 +79,8 @@ def load_library():
         lib.nkfb_conn.argtypes = [vp, P(OpT), vp, i32, i64, i32, P(dbl), vp, vp, vp]
         lib.nkfb_logpsi.argtypes = [vp, P(RbmT), P(OpT), vp, i64, P(dbl), vp, vp]
         lib.nkfb_sample.argtypes = [vp, P(RbmT), P(OpT), P(SampleCfgT), vp, vp, vp, vp]
+        lib.nkfb_sample_workspace_bytes.argtypes = [i32, i32, i32]
+        lib.nkfb_sample_workspace_bytes.restype = C.c_size_t
         lib.nkfb_infidelity_fwd.argtypes = [vp, P(RbmT), P(RbmT), P(OpT), P(OpT), P(OpT), vp, vp, i64,
                                             P(dbl), dbl, vp, vp, vp, vp, vp]
         lib.nkfb_infidelity_grad.argtypes = [vp, P(RbmT), P(OpT), vp, vp, i64, P(dbl), dbl, vp, vp, vp, vp, vp]
@@ -261,7 +264,7 @@ class Handle:
     # ---------------------------------------------------------------- sampler
     def sample(self, net: RbmSpec, chain_state, chain_length, n_discard, sweep_size, seed, local_states,
                op: OpSpec | None = None, chain_offset=0, step_offset=0, site_mode=0, init_random=False,
-               n_accepted=None, out=None):
+               n_accepted=None, out=None, workspace=None):
         n_chains, W32 = chain_state.shape
         if out is None:
             out = torch.empty((n_chains, chain_length, W32), dtype=torch.int32, device=chain_state.device)
@@ -271,12 +274,20 @@ class Handle:
         cfg.chain_offset, cfg.step_offset = int(chain_offset), int(step_offset)
         cfg.local_states = _ls(local_states)
         cfg.init_random = 1 if init_random else 0
+        if workspace is not None:
+            cfg.workspace = workspace.data_ptr()
+            cfg.workspace_bytes = workspace.numel() * workspace.element_size()
         ns = net.struct()
         os_ = op.struct() if op is not None else None
         self._check(self.lib.nkfb_sample(self.h, C.byref(ns), C.byref(os_) if os_ is not None else None,
                                          C.byref(cfg), _ptr(chain_state), _ptr(out), _ptr(n_accepted), _stream()),
                     "nkfb_sample")
         return out
+
+    def sample_workspace(self, net: RbmSpec):
+        """Scratch for the sampler's pre-scaled parameter copy (one per concurrently sampled state)."""
+        nbytes = int(self.lib.nkfb_sample_workspace_bytes(net.N, net.M, net.code))
+        return torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
 
     # ---------------------------------------------------------------- estimator / gradient
     def infidelity_fwd(self, psi: RbmSpec, phi: RbmSpec, sigma, eta, local_states, cv_coeff, op1=None, op2=None,

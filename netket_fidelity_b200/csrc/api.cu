@@ -134,6 +134,8 @@ __global__ void microbench_kernel(int iters, float *sink) {
   float a = 0.001f * (threadIdx.x + 1), b = 0.5f + 0.001f * threadIdx.x, c = 1.0f + 0.01f * threadIdx.x,
         d = 0.25f + 0.002f * threadIdx.x;
   float e = a + 0.1f, f = b + 0.1f, g = c + 0.1f, hh = d + 0.1f;
+  const float m1 = 0.999f + 1e-9f * (float)iters, m2 = 0.001f + 1e-9f * (float)iters;  // runtime values: no immediates
+  float2 A2 = make_float2(a, e), B2 = make_float2(b, f), C2 = make_float2(c, g), D2 = make_float2(d, hh);
   for (int i = 0; i < iters; ++i) {
     if (KIND == 0) {
       a = mufu_ex2(a); b = mufu_ex2(b); c = mufu_ex2(c); d = mufu_ex2(d);
@@ -147,13 +149,22 @@ __global__ void microbench_kernel(int iters, float *sink) {
       e = mufu_lg2(e); f = mufu_lg2(f); g = mufu_lg2(g); hh = mufu_lg2(hh);
       a = fabsf(a) + 1.f; b = fabsf(b) + 1.f; c = fabsf(c) + 1.f; d = fabsf(d) + 1.f;
       e = fabsf(e) + 1.f; f = fabsf(f) + 1.f; g = fabsf(g) + 1.f; hh = fabsf(hh) + 1.f;
-    } else {
+    } else if (KIND == 3) {
       a = fmaf(a, 0.999f, 0.001f); b = fmaf(b, 0.999f, 0.001f); c = fmaf(c, 0.999f, 0.001f);
       d = fmaf(d, 0.999f, 0.001f); e = fmaf(e, 0.999f, 0.001f); f = fmaf(f, 0.999f, 0.001f);
       g = fmaf(g, 0.999f, 0.001f); hh = fmaf(hh, 0.999f, 0.001f);
+    } else if (KIND == 4) {  // three-register FFMA
+      a = fmaf(a, m1, m2); b = fmaf(b, m1, m2); c = fmaf(c, m1, m2); d = fmaf(d, m1, m2);
+      e = fmaf(e, m1, m2); f = fmaf(f, m1, m2); g = fmaf(g, m1, m2); hh = fmaf(hh, m1, m2);
+    } else {  // KIND 5: packed FFMA2 (2 FMAs per lane per instruction), 8 instructions = 16 FMAs
+      float2 A = make_float2(a, b), B = make_float2(c, d), Cc = make_float2(e, f), D = make_float2(g, hh);
+      const float2 M1 = make_float2(m1, m1), M2 = make_float2(m2, m2);
+      A = __ffma2_rn(A, M1, M2); B = __ffma2_rn(B, M1, M2); Cc = __ffma2_rn(Cc, M1, M2); D = __ffma2_rn(D, M1, M2);
+      A2 = __ffma2_rn(A2, M1, M2); B2 = __ffma2_rn(B2, M1, M2); C2 = __ffma2_rn(C2, M1, M2); D2 = __ffma2_rn(D2, M1, M2);
+      a = A.x; b = A.y; c = B.x; d = B.y; e = Cc.x; f = Cc.y; g = D.x; hh = D.y;
     }
   }
-  float r = a + b + c + d + e + f + g + hh;
+  float r = a + b + c + d + e + f + g + hh + A2.x + A2.y + B2.x + B2.y + C2.x + C2.y + D2.x + D2.y;
   if (r == 123.456f) sink[0] = r;
 }
 
@@ -320,14 +331,16 @@ extern "C" int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops
       case 0: microbench_kernel<0><<<grid, block, 0, st>>>(iters, sink); break;
       case 1: microbench_kernel<1><<<grid, block, 0, st>>>(iters, sink); break;
       case 2: microbench_kernel<2><<<grid, block, 0, st>>>(iters, sink); break;
-      default: microbench_kernel<3><<<grid, block, 0, st>>>(iters, sink); break;
+      case 3: microbench_kernel<3><<<grid, block, 0, st>>>(iters, sink); break;
+      case 4: microbench_kernel<4><<<grid, block, 0, st>>>(iters, sink); break;
+      default: microbench_kernel<5><<<grid, block, 0, st>>>(iters, sink); break;
     }
     h->launches++;
     NKFB_CHECK_CUDA(h, cudaEventRecord(e1, st));
     NKFB_CHECK_CUDA(h, cudaEventSynchronize(e1));
     float ms = 0;
     NKFB_CHECK_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
-    double ops = (double)grid * block * 8.0 * iters / (ms * 1e-3);
+    double ops = (double)grid * block * (kind == 5 ? 16.0 : 8.0) * iters / (ms * 1e-3);
     if (rep > 0 && ops > best) best = ops;
   }
   cudaEventDestroy(e0);

@@ -13,7 +13,10 @@
 // Composite target (|sum_c mel_c phi(x'_c)|^2, c over the connected elements of a gate or
 // of an Ising-type operator): one warp per chain, complex log cosh for every connected
 // configuration of the proposal.
-#include "sampler_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+#include "sampler_plain.cuh"
 
 namespace nkfb {
 
@@ -227,23 +230,52 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_composite_kernel(NetDe
 
 // ------------------------------------------------------------------ dispatch
 // plain-target kernels are instantiated per (real type, lane-group width) in sampler_inst.cu
-int dispatch_plain_f32_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f32_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f32_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f32_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f64_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f64_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f64_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
-int dispatch_plain_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, cudaStream_t);
+int dispatch_plain_f32_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f32_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f32_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f32_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f64_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f64_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f64_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
+int dispatch_plain_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
 
 // lane-group width with the least padded work (ties -> wider group); K = ceil(M / L) <= 16 (32 for L = 32)
-static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
-  const int M = net->n_hidden;
+static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, void *ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  const int M = net->n_hidden, N = net->n_visible;
+  // pre-scaled parameter copy (X = 2 log2e Re, Y = 2 Im) in the caller's scratch or the handle's
+  const size_t need = sampler_ws_reals(N, M) * (net->dtype == NKFB_F32 ? 4 : 8);
+  if (ws) {
+    if (ws_bytes < need) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler workspace too small: %zu < %zu bytes", ws_bytes, need);
+  } else {
+    if (h->ws_bytes < need) {
+      if (h->ws) cudaFree(h->ws);
+      h->ws = nullptr;
+      h->ws_bytes = 0;
+      NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws, need));
+      h->ws_bytes = need;
+    }
+    ws = h->ws;
+  }
+  {
+    const int64_t tot = (int64_t)N * M + M + N;
+    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+    if (net->dtype == NKFB_F32)
+      prep_sampler_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), (float *)ws);
+    else
+      prep_sampler_params<double><<<grid, 256, 0, st>>>(make_netdev<double>(net), (double *)ws);
+    NKFB_LAUNCHED(h);
+  }
   int bestL = 0, bestWork = 1 << 30;
   const int Ls[4] = {32, 16, 8, 4};
+  const char *forceL = getenv("NKFB_SAMP_L");  // tuning override
   for (int q = 0; q < 4; ++q) {
     const int L = Ls[q], K = (M + L - 1) / L;
     if (K > 16) continue;
+    if (forceL && atoi(forceL) == L) {
+      bestL = L;
+      break;
+    }
     if (L * K < bestWork) {
       bestWork = L * K;
       bestL = L;
@@ -256,10 +288,10 @@ static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs
   const int K = (M + bestL - 1) / bestL;
   const bool f32 = net->dtype == NKFB_F32;
   switch (bestL) {
-    case 32: return f32 ? dispatch_plain_f32_L32(h, net, a, K, st) : dispatch_plain_f64_L32(h, net, a, K, st);
-    case 16: return f32 ? dispatch_plain_f32_L16(h, net, a, K, st) : dispatch_plain_f64_L16(h, net, a, K, st);
-    case 8: return f32 ? dispatch_plain_f32_L8(h, net, a, K, st) : dispatch_plain_f64_L8(h, net, a, K, st);
-    default: return f32 ? dispatch_plain_f32_L4(h, net, a, K, st) : dispatch_plain_f64_L4(h, net, a, K, st);
+    case 32: return f32 ? dispatch_plain_f32_L32(h, net, a, K, ws, st) : dispatch_plain_f64_L32(h, net, a, K, ws, st);
+    case 16: return f32 ? dispatch_plain_f32_L16(h, net, a, K, ws, st) : dispatch_plain_f64_L16(h, net, a, K, ws, st);
+    case 8: return f32 ? dispatch_plain_f32_L8(h, net, a, K, ws, st) : dispatch_plain_f64_L8(h, net, a, K, ws, st);
+    default: return f32 ? dispatch_plain_f32_L4(h, net, a, K, ws, st) : dispatch_plain_f64_L4(h, net, a, K, ws, st);
   }
 }
 
@@ -324,6 +356,11 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   const bool composite = op && op->kind != NKFB_OP_NONE;
   if ((uint64_t)(cfg->n_discard + (int64_t)cfg->chain_length) * (uint64_t)cfg->sweep_size >= (1ull << 31))
     NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "more than 2^31 Metropolis steps in one call");
-  if (!composite) return dispatch_plain(h, net, a, st);
+  if (!composite) return dispatch_plain(h, net, a, cfg->workspace, (size_t)cfg->workspace_bytes, st);
   return net->dtype == NKFB_F32 ? dispatch_composite<float>(h, net, a, st) : dispatch_composite<double>(h, net, a, st);
+}
+
+extern "C" size_t nkfb_sample_workspace_bytes(int n_visible, int n_hidden, int dtype) {
+  if (n_visible < 1 || n_hidden < 1) return 0;
+  return sampler_ws_reals(n_visible, n_hidden) * (dtype == NKFB_F32 ? 4 : 8);
 }

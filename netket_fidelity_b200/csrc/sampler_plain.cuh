@@ -2,65 +2,128 @@
 //
 // Template parameters: R real type; L lanes per chain group (4/8/16/32); K hidden units per
 // lane, EXACT (K = ceil(M / L): no per-unit predicates in the Metropolis loop, only the last
-// unit of a lane can fall outside M and it is handled by one predicated load of W);
+// unit of a lane can fall outside M and it is handled by one predicated load);
 // C chains per lane group (they share the row W[i, :] when the site sequence is shared).
+//
+// The kernel works on PRE-SCALED parameters written by prep_sampler_params into a scratch
+// buffer:  X = 2 log2(e) Re(theta),  Y = 2 Im(theta), so that per hidden unit
+//     log2 |cosh theta|^2 + 2 = |X| + log2(1 + t^2 + 2 t cos Y),   t = 2^(-|X|)
+// costs MUFU.EX2 + MUFU.COS (+ MUFU.LG2 per four units: the log arguments are multiplied first)
+// and, on sm_100, five packed-FP32 instructions per PAIR of units (FFMA2 / FMUL2: the (re, im)
+// pair of a unit and the pair (unit k, unit k+1) are both natural float2 operands).
 #pragma once
 
 #include "sampler_common.cuh"
 
 namespace nkfb {
 
+// ------------------------------------------------------------------ packed pair arithmetic
 template <typename R>
-struct Vec2;
+struct P2;
 template <>
-struct Vec2<float> {
-  using type = float2;
+struct P2<float> {
+  using V = float2;
+  static __device__ __forceinline__ V mk(float a, float b) { return make_float2(a, b); }
+  static __device__ __forceinline__ V fma(V a, V b, V c) { return __ffma2_rn(a, b, c); }
+  static __device__ __forceinline__ V mul(V a, V b) { return __fmul2_rn(a, b); }
+  static __device__ __forceinline__ float ex2(float x) { return mufu_ex2(x); }
+  static __device__ __forceinline__ float cosr(float x) { return mufu_cos(x); }
+  static __device__ __forceinline__ float lg2(float x) { return mufu_lg2(x); }
 };
 template <>
-struct Vec2<double> {
-  using type = double2;
+struct P2<double> {
+  using V = double2;
+  static __device__ __forceinline__ V mk(double a, double b) { return make_double2(a, b); }
+  static __device__ __forceinline__ V fma(V a, V b, V c) { return make_double2(::fma(a.x, b.x, c.x), ::fma(a.y, b.y, c.y)); }
+  static __device__ __forceinline__ V mul(V a, V b) { return make_double2(a.x * b.x, a.y * b.y); }
+  static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
+  static __device__ __forceinline__ double cosr(double x) { return cos(x); }
+  static __device__ __forceinline__ double lg2(double x) { return log2(x); }
 };
+
+__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+
+// scratch layout (reals of type R): Wt (N*M pairs) | bt (M pairs) | ar2 (N)
+inline size_t sampler_ws_reals(int N, int M) { return 2 * (size_t)N * M + 2 * (size_t)M + (size_t)N; }
+
+template <typename R>
+__global__ void prep_sampler_params(NetDev<R> net, R *ws) {
+  const int N = net.N, M = net.M;
+  const int64_t nW = (int64_t)N * M;
+  const R sx = (R)(2.0 * LOG2E);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nW + M + N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nW) {
+      ws[2 * i] = sx * net.W[2 * i];
+      ws[2 * i + 1] = R(2) * net.W[2 * i + 1];
+    } else if (i < nW + M) {
+      const int64_t j = i - nW;
+      ws[2 * i] = net.b ? sx * net.b[2 * j] : R(0);
+      ws[2 * i + 1] = net.b ? R(2) * net.b[2 * j + 1] : R(0);
+    } else {
+      const int64_t k = i - nW - M;
+      ws[2 * (nW + M) + k] = net.a ? sx * net.a[2 * k] : R(0);
+    }
+  }
+}
+
+// sum over the lane's K units of |X| + log2(1 + t^2 + 2 t cos Y)
+template <typename R, int K>
+__device__ __forceinline__ R lane_lc(const typename P2<R>::V (&p)[K]) {
+  using P = P2<R>;
+  using V = typename P::V;
+  R sumabs = R(0), lg = R(0);
+  V prod = P::mk(R(1), R(1));
+#pragma unroll
+  for (int k = 0; k + 1 < K; k += 2) {
+    const R a0 = abs_(p[k].x), a1 = abs_(p[k + 1].x);
+    const V T = P::mk(P::ex2(-a0), P::ex2(-a1));
+    const V Cc = P::mk(P::cosr(p[k].y), P::cosr(p[k + 1].y));
+    const V u = P::fma(P::mk(R(2), R(2)), Cc, T);
+    const V s = P::fma(T, u, P::mk(R(1), R(1)));
+    prod = P::mul(prod, s);
+    sumabs += a0;
+    sumabs += a1;
+    if (((k + 2) & 3) == 0) {  // every four units: one log2 for the product of four arguments
+      lg += P::lg2(prod.x * prod.y);
+      prod = P::mk(R(1), R(1));
+    }
+  }
+  if (K & 1) {
+    const R a0 = abs_(p[K - 1].x);
+    const R t = P::ex2(-a0), c = P::cosr(p[K - 1].y);
+    prod.x *= ::fma(t, ::fma(R(2), c, t), R(1));
+    sumabs += a0;
+  }
+  if ((K & 3) != 0) lg += P::lg2(prod.x * prod.y);
+  return sumabs + lg;
+}
 
 template <typename R, int L, int K>
 struct RowLoader {
-  using V2 = typename Vec2<R>::type;
-  const V2 *W;  // complex rows, M per row
+  using V = typename P2<R>::V;
+  const V *W;  // pre-scaled complex rows, M per row
   int M, l;
   bool last_ok;
-  __device__ __forceinline__ RowLoader(const R *Wp, int M_, int l_) : W(reinterpret_cast<const V2 *>(Wp)), M(M_), l(l_) {
+  __device__ __forceinline__ RowLoader(const R *Wp, int M_, int l_) : W(reinterpret_cast<const V *>(Wp)), M(M_), l(l_) {
     last_ok = (l + L * (K - 1)) < M;
   }
-  __device__ __forceinline__ void load(int row, R (&wr)[K], R (&wi)[K]) const {
-    const V2 *p = W + (int64_t)row * M + l;
+  __device__ __forceinline__ void load(int row, V (&w)[K]) const {
+    const V *p = W + (int64_t)row * M + l;
 #pragma unroll
-    for (int k = 0; k < K - 1; ++k) {
-      const V2 v = __ldg(p + L * k);
-      wr[k] = v.x;
-      wi[k] = v.y;
-    }
-    V2 v;
-    v.x = R(0);
-    v.y = R(0);
+    for (int k = 0; k < K - 1; ++k) w[k] = __ldg(p + L * k);
+    V v = P2<R>::mk(R(0), R(0));
     if (last_ok) v = __ldg(p + L * (K - 1));
-    wr[K - 1] = v.x;
-    wi[K - 1] = v.y;
+    w[K - 1] = v;
   }
 };
 
-// sum_j log2|cosh(theta_j)| + (number of units), in the log2 domain, for the K units of this lane
-template <typename R, int K>
-__device__ __forceinline__ R lane_logcosh2(const R (&xr)[K], const R (&xi)[K]) {
-  R sumabs = R(0), prod = R(1), lg = R(0);
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    SMath<R>::unit(xr[k], xi[k], sumabs, prod);
-    if ((k & 3) == 3 || k == K - 1) lg += SMath<R>::flush(prod);
-  }
-  return SMath<R>::finish(sumabs, lg);
-}
-
-template <typename R, int L, int K, int C>
-__global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R> net, SampArgs a) {
+template <typename R, int L, int K, int C, int MB>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_plain_kernel(NetDev<R> net, const R *ws, const R s0,
+                                                                            const R s1, SampArgs a) {
+  using P = P2<R>;
+  using V = typename P::V;
   constexpr int G = 32 / L;      // chain groups per warp
   constexpr int NCH = G * C;     // chains per warp
   constexpr int BLK = 32 / NCH;  // Philox blocks per chain per RNG batch
@@ -73,8 +136,10 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
   const int64_t warp_global = (int64_t)blockIdx.x * SAMP_WARPS + warp;
   const int64_t chain0 = warp_global * NCH;  // first local chain of this warp
   if (chain0 >= a.n_chains) return;
-  const R s0 = (R)a.s0, s1 = (R)a.s1, ssum = s0 + s1;
-  const RowLoader<R, L, K> rows(net.W, M, l);
+  const R ssum = s0 + s1;
+  const RowLoader<R, L, K> rows(ws, M, l);
+  const V *bt = reinterpret_cast<const V *>(ws) + (size_t)N * M;
+  const R *ar2 = ws + 2 * ((size_t)N * M + M);
 
   // ---- load / initialise configurations
   for (int idx = lane; idx < NCH * W32; idx += 32) {
@@ -95,40 +160,34 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
   }
   __syncwarp();
 
-  // ---- theta from scratch: theta_j = b_j + sum_i x_i W_ij
-  R thr[C][K], thi[C][K];
+  // ---- (scaled) theta from scratch: theta_j = b_j + sum_i x_i W_ij
+  V th[C][K];
   {
-    R br[K], bi[K];
+    V bb[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int j = l + L * k;
-      br[k] = (j < M && net.b) ? net.b[2 * j] : R(0);
-      bi[k] = (j < M && net.b) ? net.b[2 * j + 1] : R(0);
+      bb[k] = (j < M) ? bt[j] : P::mk(R(0), R(0));
     }
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        thr[c][k] = br[k];
-        thi[c][k] = bi[k];
-      }
+      for (int k = 0; k < K; ++k) th[c][k] = bb[k];
   }
   for (int i = 0; i < N; ++i) {
-    R wr[K], wi[K];
-    rows.load(i, wr, wi);
+    V w[K];
+    rows.load(i, w);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const R xv = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+      const V xx = P::mk(xv, xv);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        thr[c][k] = fma(xv, wr[k], thr[c][k]);
-        thi[c][k] = fma(xv, wi[k], thi[c][k]);
-      }
+      for (int k = 0; k < K; ++k) th[c][k] = P::fma(xx, w[k], th[c][k]);
     }
   }
   R lc[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) lc[c] = group_sum<L>(lane_logcosh2<R, K>(thr[c], thi[c]));
+  for (int c = 0; c < C; ++c) lc[c] = group_sum<L>(lane_lc<R, K>(th[c]));
 
   unsigned n_acc = 0;
   const uint32_t n_steps = (uint32_t)(a.n_discard + a.chain_length) * (uint32_t)a.sweep_size;
@@ -138,10 +197,11 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
   R lu[4] = {R(0), R(0), R(0), R(0)};
   int until_emit = a.sweep_size, sweep = 0;
   const bool shared_sites = (a.site_mode == 0);
+  const R invL = R(1) / R(L);
 
   for (uint32_t s = 0; s < n_steps; ++s) {
-    const uint32_t pos = s + phase;           // steps since batch0
-    const int tb = (int)(pos & (SB - 1));     // position inside the RNG batch
+    const uint32_t pos = s + phase;        // steps since batch0
+    const int tb = (int)(pos & (SB - 1));  // position inside the RNG batch
     if (tb == 0 || s == 0) {
       // refill: lane r serves chain slot r % NCH with Philox block (batch start)/4 + r / NCH
       const uint64_t bb = batch0 + (uint64_t)(pos - tb);
@@ -166,48 +226,77 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
     const uint32_t my_rs = sel4(rs, comp);
     const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
 
-    R wr[K], wi[K];
+    // ---- proposal site and the row W[site, :]
+    V w[K];
     int site = 0;
     R ar = R(0);
     if (shared_sites) {
       site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
-      rows.load(site, wr, wi);
-      if (net.a) ar = __ldg(net.a + 2 * site);
+      rows.load(site, w);
+      ar = __ldg(ar2 + site);
     }
 
+    // ---- phase 1: per-lane partial sums for every chain of the group
+    R part[C], dd[C], logu[C];
+    uint32_t word[C];
+    int sitec[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int slot = g * C + c;
       const int src = slot + NCH * bi;
-      const R logu = __shfl_sync(0xffffffffu, my_lu, src);
+      logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
       if (!shared_sites) {
         site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
-        rows.load(site, wr, wi);
-        ar = net.a ? __ldg(net.a + 2 * site) : R(0);
+        rows.load(site, w);
+        ar = __ldg(ar2 + site);
       }
-      const uint32_t word = sig[slot * W32 + (site >> 5)];
-      const R xold = ((word >> (site & 31)) & 1u) ? s1 : s0;
+      sitec[c] = site;
+      word[c] = sig[slot * W32 + (site >> 5)];
+      const R xold = ((word[c] >> (site & 31)) & 1u) ? s1 : s0;
       const R d = ssum - R(2) * xold;  // x_new - x_old
-      R pr[K], pi[K];
+      dd[c] = d;
+      const V d2 = P::mk(d, d);
+      V p[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        pr[k] = fma(d, wr[k], thr[c][k]);
-        pi[k] = fma(d, wi[k], thi[c][k]);
-      }
-      const R lcn = group_sum<L>(lane_logcosh2<R, K>(pr, pi));
-      // log2 of the acceptance ratio |psi(x')|^2 / |psi(x)|^2
-      const R dl = R(2) * (lcn - lc[c]) + R(2.0 * LOG2E) * d * ar;
-      const bool acc = (logu < dl) && (chain0 + slot < a.n_chains);
-      const R de = acc ? d : R(0);
+      for (int k = 0; k < K; ++k) p[k] = P::fma(d2, w[k], th[c][k]);
+      // the visible-bias term d * ar is spread over the L lanes so that the butterfly sum carries it
+      part[c] = ::fma(d * ar, invL, lane_lc<R, K>(p));
+      if (!shared_sites) {
+        // per-chain sites: the row differs from chain to chain, so finish this chain now
+        const R lcn = group_sum<L>(part[c]);
+        const bool acc = (logu[c] < lcn - lc[c]) && (chain0 + slot < a.n_chains);
+        const R de = acc ? d : R(0);
+        const V de2 = P::mk(de, de);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        thr[c][k] = fma(de, wr[k], thr[c][k]);
-        thi[c][k] = fma(de, wi[k], thi[c][k]);
+        for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
+        lc[c] = acc ? lcn - d * ar : lc[c];
+        if (acc && l == 0) {
+          sig[slot * W32 + (site >> 5)] = word[c] ^ (1u << (site & 31));
+          ++n_acc;
+        }
       }
-      lc[c] = acc ? lcn : lc[c];
-      if (acc && l == 0) {
-        sig[slot * W32 + (site >> 5)] = word ^ (1u << (site & 31));
-        ++n_acc;
+    }
+    if (shared_sites) {
+      // ---- phase 2: the C butterfly reductions are independent and pipeline through the shuffle unit
+#pragma unroll
+      for (int m = L / 2; m > 0; m >>= 1)
+#pragma unroll
+        for (int c = 0; c < C; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], m);
+      // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 / |psi(x)|^2
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const R d = dd[c];
+        const bool acc = (logu[c] < part[c] - lc[c]) && (chain0 + slot < a.n_chains);
+        const R de = acc ? d : R(0);
+        const V de2 = P::mk(de, de);
+#pragma unroll
+        for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
+        lc[c] = acc ? part[c] - d * ar : lc[c];
+        if (acc && l == 0) {
+          sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
+          ++n_acc;
+        }
       }
     }
     __syncwarp();
@@ -217,18 +306,18 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
       if (sweep >= a.n_discard) {
         const int ts = sweep - a.n_discard;
         for (int idx = lane; idx < NCH * W32; idx += 32) {
-          const int slot = idx / W32, w = idx - slot * W32;
+          const int slot = idx / W32, w32 = idx - slot * W32;
           const int64_t ch = chain0 + slot;
-          if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w] = sig[idx];
+          if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w32] = sig[idx];
         }
       }
       ++sweep;
     }
   }
   for (int idx = lane; idx < NCH * W32; idx += 32) {
-    const int slot = idx / W32, w = idx - slot * W32;
+    const int slot = idx / W32, w32 = idx - slot * W32;
     const int64_t ch = chain0 + slot;
-    if (ch < a.n_chains) a.chain_state[ch * W32 + w] = sig[idx];
+    if (ch < a.n_chains) a.chain_state[ch * W32 + w32] = sig[idx];
   }
   if (a.n_accepted) {
     n_acc = warp_sum(n_acc);
@@ -236,19 +325,20 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_plain_kernel(NetDev<R>
   }
 }
 
-template <typename R, int L, int K, int C>
-static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
+template <typename R, int L, int K, int C, int MB = 1>
+static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws, cudaStream_t st) {
   constexpr int NCH = (32 / L) * C;
   const int W32 = (net->n_visible + 31) >> 5;
   const int64_t warps = (a.n_chains + NCH - 1) / NCH;
   const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
   const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
   if (smem > 48 * 1024) {
-    cudaError_t rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, K, C>,
+    cudaError_t rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, K, C, MB>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   }
-  sample_plain_kernel<R, L, K, C><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(make_netdev<R>(net), a);
+  sample_plain_kernel<R, L, K, C, MB><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
+      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
   NKFB_LAUNCHED(h);
   return NKFB_OK;
 }

@@ -1,0 +1,34 @@
+"""Times the plain-target sampler launch of a workload for each tuning variant
+(NKFB_SAMP_VARIANT, only compiled in with `make TUNE=-DNKFB_TUNE`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from netket_fidelity_b200 import _native as nv  # noqa: E402
+from netket_fidelity_b200.workloads import make_workload, random_rbm  # noqa: E402
+
+w = make_workload(sys.argv[1] if len(sys.argv) > 1 else "C4")
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4, 5, 6]
+N, M = w["N"], w["M"]
+h = nv.get_handle(0)
+net = nv.RbmSpec(*[t.cuda() if t is not None else None for t in random_rbm(N, M, 1234)])
+W32 = (N + 31) // 32
+state = torch.zeros((w["n_chains"], W32), dtype=torch.int32, device="cuda")
+out = torch.empty((w["n_chains"], w["chain_length"], W32), dtype=torch.int32, device="cuda")
+mufu = h.microbench(0, 2048)
+for v in variants:
+    os.environ["NKFB_SAMP_VARIANT"] = str(v)
+    ts = []
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h.sample(net, state, w["chain_length"], 5, N, 7, (-1.0, 1.0), init_random=(rep == 0), out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = min(ts[1:])
+    evals = w["n_chains"] * (5 + w["chain_length"]) * N * M
+    print(f"variant {v}: {t:.3f} ms  {evals / t / 1e6:.1f} G evals/s  frac of MUFU roofline "
+          f"{evals * 2.25 / (t * 1e-3) / mufu:.3f}", flush=True)
