@@ -1,0 +1,83 @@
+"""Host side of `MCState.expect` / `MCState.expect_and_grad` for the infidelity operators --
+replaces the plum-dispatched overloads of infidelity/overlap/expect.py:14-55 and
+infidelity/overlap_U/expect.py:16-67, and the jitted `infidelity_sampling_MCState` bodies
+(:58-130 / :70-161) with two CUDA kernels (nkfb_infidelity_fwd, nkfb_infidelity_grad) and,
+when torch.distributed is initialised, two all-reduces (8 doubles, then the 2P-double
+gradient accumulator) standing in for NetKet's MPI means (expect.py:126 / :157).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from .. import _native as nv
+from ..nk.vqs import MCState
+from .overlap.operator import InfidelityOperatorStandard
+from .overlap_U.operator import InfidelityOperatorUPsi
+
+
+def _allreduce(t):
+    d = torch.distributed
+    if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+
+
+def infidelity_expect(vstate: MCState, op, return_grad: bool):
+    if op.hilbert != vstate.hilbert:
+        raise TypeError("Hilbert spaces should match")
+    target = op.target
+    if not isinstance(target, MCState):
+        raise TypeError("The target of an infidelity operator evaluated on an MCState must be an MCState")
+    dev = vstate.device
+    if isinstance(op, InfidelityOperatorStandard):
+        # overlap/expect.py:85: log Phi(sigma) + log psi(eta) - log psi(sigma) - log Phi(eta)
+        op1 = op4 = target._op_spec()
+        op2 = None
+    else:
+        # overlap_U/expect.py:108-116
+        if target._unitary is not None:
+            raise TypeError("InfidelityOperatorUPsi needs a plain target state")
+        for o in (op._U, op._U_dagger):
+            if not hasattr(o, "_spec"):
+                raise TypeError("U and U_dagger must be operators from netket_fidelity_b200.operator "
+                                "(their connected elements are generated inside the CUDA kernels)")
+        op1, op2, op4 = op._U._spec(dev), op._U_dagger._spec(dev), None
+    if vstate._spec().code != target._spec().code:
+        raise TypeError("the variational state and the target must share a parameter precision")
+    sigma = vstate.samples_packed()
+    eta = target.samples_packed()
+    if sigma.shape != eta.shape:
+        raise ValueError(f"both states need the same number of samples per rank, got {tuple(sigma.shape[:2])} "
+                         f"and {tuple(eta.shape[:2])}")
+    h = vstate._h
+    W32 = sigma.shape[-1]
+    psi, phi = vstate._spec(), target._spec()
+    ls = vstate._ls
+    acc = torch.zeros((8 + 2 * vstate._flat.numel(),), dtype=torch.float64, device=dev)
+    sums, gacc = acc[:8], acc[8:]
+    log_val, L, rho1, _ = h.infidelity_fwd(psi, phi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff,
+                                           op1, op2, op4, sums=sums)
+    _allreduce(sums)
+    # n_chains = sigma_t.shape[-2] (overlap/expect.py:72): the reference hands the CHAIN LENGTH to
+    # nkjax.expect as "n_chains"; mean, variance and gradient do not depend on it
+    F_stats = vstate._stats_of(L, eta.shape[-2], sums=sums)
+    I_stats = F_stats.replace(mean=1.0 - F_stats.mean)
+    if not return_grad:
+        return I_stats
+    h.infidelity_grad(psi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff, log_val, rho1, sums, op2=op2,
+                      grad_acc=gacc)
+    _allreduce(gacc)
+    flat = h.grad_finalize(gacc, sums, vstate._flat.numel(), vstate._cdtype)
+    vstate._last_flat_grad = flat
+    return I_stats, vstate._tree(flat)
+
+
+def expect_dispatch(vstate, op, return_grad):
+    from ..renyi2 import Renyi2EntanglementEntropy, renyi2_expect
+    if isinstance(op, (InfidelityOperatorStandard, InfidelityOperatorUPsi)):
+        return infidelity_expect(vstate, op, return_grad)
+    if isinstance(op, Renyi2EntanglementEntropy):
+        if return_grad:
+            raise NotImplementedError("gradient of the Renyi-2 entropy")
+        return renyi2_expect(vstate, op)
+    raise TypeError(f"no GPU expectation-value kernel for operators of type {type(op).__name__}")

@@ -1,0 +1,296 @@
+"""MCState (NetKet `nk.vqs.MCState`) for an RBM ansatz, backed by the CUDA kernels.
+
+Only what the infidelity hot path uses: `.samples`, `.reset()`, `.parameters` (get/set),
+`.variables`, `.model_state`, `.n_samples`, `.chain_length`, `.n_discard_per_chain`,
+`.log_value(x)`, `.expect(op)`, `.expect_and_grad(op)`, `.to_array()` (small N).
+
+Parameters live in ONE flat complex device buffer laid out [bias | kernel | visible_bias]
+(the jax leaf order of the NetKet RBM parameter dict, which is also the layout of the
+gradient returned by the kernels); `.parameters` returns views into it.  A real-parameter
+model (`param_dtype=float`) keeps zero imaginary parts; its gradient is the real part of
+the complex-convention gradient.
+
+`variables["unitary"]` (reference: utils/sampling_Ustate.py:7-31) turns the state into
+U|phi>: log_value, sampling and the estimator then use log sum_c mel_c phi(x'_c).
+"""
+
+from __future__ import annotations
+
+import itertools
+import os
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+from .stats import Stats, stats_from_partials
+
+_seed_counter = itertools.count()
+
+
+def _world():
+    d = torch.distributed
+    if d.is_available() and d.is_initialized():
+        return d.get_world_size(), d.get_rank()
+    return 1, 0
+
+
+class MCState:
+    def __init__(self, sampler, model=None, *, n_samples=None, n_samples_per_rank=None, n_discard_per_chain=None,
+                 chunk_size=None, variables=None, seed=None, sampler_seed=None, device=None, apply_fun=None):
+        if chunk_size is not None:
+            raise NotImplementedError("chunk_size: the CUDA kernels tile the samples internally")
+        if apply_fun is not None:
+            raise TypeError("only the RBM ansatz is implemented on the GPU hot path; pass `model=`")
+        if not torch.cuda.is_available():
+            raise nv.NkfbError("no CUDA device: netket_fidelity_b200 has no CPU fallback")
+        self._h = nv.get_handle(device)
+        self.device = self._h.device
+        self.sampler = sampler
+        self.hilbert = sampler.hilbert
+        self.model = model
+        self._world, self._rank = _world()
+        N = self.hilbert.size
+        self._N = N
+        self._ls = tuple(self.hilbert.local_states)
+
+        # --- sample counts: n_samples rounded up to a multiple of the total number of chains
+        n_chains = sampler.n_chains
+        if n_samples is not None and n_samples_per_rank is not None:
+            raise ValueError("Only one argument between `n_samples` and `n_samples_per_rank` can be specified")
+        if n_samples_per_rank is not None:
+            n_samples = int(n_samples_per_rank) * self._world
+        if n_samples is None:
+            n_samples = 1000
+        self._chain_length = max(1, -(-int(n_samples) // n_chains))
+        self._n_chains = n_chains
+        self._n_chains_local = sampler.n_chains_per_rank
+        self.n_discard_per_chain = 5 if n_discard_per_chain is None else int(n_discard_per_chain)
+
+        # --- parameters
+        if seed is None:
+            seed = int.from_bytes(os.urandom(4), "little") + next(_seed_counter)
+        self._seed = int(seed)
+        self._sampler_seed = int(sampler_seed) if sampler_seed is not None else (self._seed * 2654435761 + 12345) % (1 << 63)
+        self._unitary = None
+        if variables is not None:
+            params = variables["params"]
+            self._unitary = variables.get("unitary", None)
+            if model is None:
+                raise ValueError("`model` is needed to interpret `variables`")
+        else:
+            params = model.init(self._seed, N, self.device)
+        self._M = params["Dense"]["kernel"].shape[1]
+        self._alloc_flat(params)
+
+        # --- chains
+        self._W32 = (N + 31) // 32
+        self._chain_state = torch.zeros((self._n_chains_local, self._W32), dtype=torch.int32, device=self.device)
+        self._chains_initialised = False
+        self._steps_done = 0
+        self._samples_packed = None
+        self._n_accepted = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._n_steps_total = 0
+        self._ws = None
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_flat(self, params):
+        N, M = self._N, self._M
+        cdt = {torch.float64: torch.complex128, torch.float32: torch.complex64,
+               torch.complex128: torch.complex128, torch.complex64: torch.complex64}[params["Dense"]["kernel"].dtype]
+        self._cdtype = cdt
+        self._flat = torch.zeros((M + N * M + N,), dtype=cdt, device=self.device)
+        self._has_bias = "bias" in params["Dense"]
+        self._has_vbias = "visible_bias" in params
+        self._set_params(params)
+
+    def _views(self):
+        N, M = self._N, self._M
+        b = self._flat[:M]
+        k = self._flat[M:M + N * M].view(N, M)
+        a = self._flat[M + N * M:]
+        return k, b, a
+
+    def _set_params(self, params):
+        k, b, a = self._views()
+        k.copy_(torch.as_tensor(params["Dense"]["kernel"]).to(self.device))
+        if self._has_bias:
+            b.copy_(torch.as_tensor(params["Dense"]["bias"]).to(self.device))
+        if self._has_vbias:
+            a.copy_(torch.as_tensor(params["visible_bias"]).to(self.device))
+        self._params_changed()
+
+    def _params_changed(self):
+        self._samples_packed = None
+
+    def _spec(self) -> nv.RbmSpec:
+        k, b, a = self._views()
+        return nv.RbmSpec(k, b if self._has_bias else None, a if self._has_vbias else None)
+
+    def _tree(self, flat):
+        """(P,) complex flat vector -> parameter-shaped dict (real part for real-parameter models)."""
+        N, M = self._N, self._M
+        real = not self.model.is_complex
+        f = (lambda t: t.real) if real else (lambda t: t)
+        out = {"Dense": {"kernel": f(flat[M:M + N * M].view(N, M))}}
+        if self._has_bias:
+            out["Dense"]["bias"] = f(flat[:M])
+        if self._has_vbias:
+            out["visible_bias"] = f(flat[M + N * M:])
+        return out
+
+    def _flatten_tree(self, tree):
+        """parameter-shaped dict -> (P,) complex flat device vector (inverse of `_tree`)."""
+        N, M = self._N, self._M
+        flat = torch.zeros_like(self._flat)
+        flat[M:M + N * M].view(N, M).copy_(torch.as_tensor(tree["Dense"]["kernel"]).to(self.device))
+        if self._has_bias:
+            flat[:M].copy_(torch.as_tensor(tree["Dense"]["bias"]).to(self.device))
+        if self._has_vbias:
+            flat[M + N * M:].copy_(torch.as_tensor(tree["visible_bias"]).to(self.device))
+        return flat
+
+    @property
+    def parameters(self):
+        return self._tree(self._flat)
+
+    @parameters.setter
+    def parameters(self, params):
+        self._set_params(params)
+
+    @property
+    def model_state(self):
+        return {} if self._unitary is None else {"unitary": self._unitary}
+
+    @property
+    def variables(self):
+        return {"params": self.parameters, **self.model_state}
+
+    @variables.setter
+    def variables(self, v):
+        self._unitary = v.get("unitary", None)
+        self._set_params(v["params"])
+
+    @property
+    def n_parameters(self):
+        n = self._N * self._M
+        return n + (self._M if self._has_bias else 0) + (self._N if self._has_vbias else 0)
+
+    # ------------------------------------------------------------------ sampling
+    @property
+    def n_samples(self):
+        return self._chain_length * self._n_chains
+
+    @property
+    def n_samples_per_rank(self):
+        return self._chain_length * self._n_chains_local
+
+    @property
+    def chain_length(self):
+        return self._chain_length
+
+    def _op_spec(self):
+        return None if self._unitary is None else self._unitary._spec(self.device)
+
+    def reset(self):
+        """Drop the sample cache; chain positions are kept (NetKet `MCState.reset`)."""
+        self._samples_packed = None
+
+    def sample(self, *, chain_length=None, n_discard_per_chain=None):
+        cl = self._chain_length if chain_length is None else int(chain_length)
+        nd = self.n_discard_per_chain if n_discard_per_chain is None else int(n_discard_per_chain)
+        net = self._spec()
+        if self._ws is None:
+            self._ws = self._h.sample_workspace(net)
+        out = self._h.sample(net, self._chain_state, cl, nd, self.sampler.sweep_size, self._sampler_seed, self._ls,
+                             op=self._op_spec(), chain_offset=self._rank * self._n_chains_local,
+                             step_offset=self._steps_done, site_mode=0 if self.sampler.site_mode == "shared" else 1,
+                             init_random=not self._chains_initialised, n_accepted=self._n_accepted,
+                             workspace=self._ws)
+        self._chains_initialised = True
+        self._steps_done += (cl + nd) * self.sampler.sweep_size
+        self._n_steps_total += (cl + nd) * self.sampler.sweep_size * self._n_chains_local
+        self._samples_packed = out
+        return out
+
+    def samples_packed(self):
+        """(n_chains_local, chain_length, W32) int32: bit-packed samples, sampled lazily."""
+        if self._samples_packed is None:
+            self.sample()
+        return self._samples_packed
+
+    @property
+    def samples(self):
+        """(n_chains_local, chain_length, N) local-state values (NetKet layout)."""
+        p = self.samples_packed()
+        x = self._h.unpack(p.view(-1, self._W32), self._N, self._ls, torch.float64)
+        return x.view(p.shape[0], p.shape[1], self._N)
+
+    @property
+    def acceptance(self):
+        return float(self._n_accepted.item()) / max(1, self._n_steps_total)
+
+    # ------------------------------------------------------------------ amplitudes
+    def log_value(self, x):
+        """log psi(x) (or log (U phi)(x) when a unitary is attached).  x: (..., N) tensor/array of local states."""
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.device)
+        shape = x.shape[:-1]
+        xf = x.reshape(-1, self._N).to(torch.float64).contiguous()
+        p = self._h.pack(xf, self._ls)
+        return self._h.logpsi(self._spec(), p, self._ls, self._op_spec()).view(shape)
+
+    def to_array(self, normalize=True):
+        if self._N > 24:
+            raise ValueError("to_array: Hilbert space too large")
+        st = torch.tensor(self.hilbert.all_states(), dtype=torch.float64, device=self.device)
+        lv = self.log_value(st).to(torch.complex128)
+        lv = lv - lv.real.max()
+        psi = torch.exp(lv)
+        if normalize:
+            psi = psi / torch.linalg.vector_norm(psi)
+        return psi
+
+    # ------------------------------------------------------------------ expectation values
+    def expect(self, op):
+        from ..infidelity.expect import expect_dispatch
+        return expect_dispatch(self, op, return_grad=False)
+
+    def expect_and_grad(self, op, *, mutable=None):
+        from ..infidelity.expect import expect_dispatch
+        return expect_dispatch(self, op, return_grad=True)
+
+    def _stats_of(self, L, n_chains_arg, mean_override=None, sums=None):
+        """nk.stats.statistics(L.reshape(n_chains_arg, -1)) with the O(S) work on the GPU."""
+        S = L.numel()
+        rows = int(n_chains_arg)
+        cols = S // rows
+        l_block = max(1, cols // 32)
+        n_blocks = cols // l_block
+        part = self._h.chain_stats(L, rows, cols, l_block, n_blocks).cpu().numpy()
+        tot, tot2 = float(part[:, 0].sum()), None
+        if sums is not None:
+            s = sums.cpu().numpy() if torch.is_tensor(sums) else np.asarray(sums)
+            n_glob = s[4]
+            mean = s[0] / n_glob
+            var = max(0.0, s[1] / n_glob - mean * mean)
+            st = stats_from_partials(part, rows, cols, l_block, n_blocks, var * rows * cols)
+            st.mean, st.variance = float(mean), float(var)
+            return st
+        mean = tot / S
+        tot2 = float(((L.double() - mean) ** 2).sum().item())
+        return stats_from_partials(part, rows, cols, l_block, n_blocks, tot2)
+
+    def __repr__(self):
+        return (f"MCState(hilbert={self.hilbert}, sampler={self.sampler}, n_samples={self.n_samples}, "
+                f"n_parameters={self.n_parameters})")
+
+
+class FullSumState:
+    """Exact (full-summation) states are OUT OF SCOPE of the GPU hot path.
+    The class exists so that `isinstance(..., FullSumState)` checks of the reference's factory
+    (infidelity/logic.py:154-161) keep their meaning; constructing one raises."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(
+            "FullSumState (exact summation over 2^N states) is not part of the B200 hot path; "
+            "use MCState, or the CPU oracle in oracle/exact.py for N <= 12 ground truth")
