@@ -22,6 +22,7 @@ from __future__ import annotations
 import torch
 
 from . import _native as nv
+from . import parallel as par
 
 
 class StepConfig:
@@ -52,14 +53,8 @@ class InfidelityStep:
         self.N, self.M, self.cfg, self.mode = N, M, cfg, mode
         self.cdtype = cdtype
         self.group = group
-        self.world, self.rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size(group)
-            self.rank = torch.distributed.get_rank(group)
-        if cfg.n_chains % self.world:
-            raise ValueError(f"n_chains={cfg.n_chains} must be divisible by the number of ranks {self.world}")
-        self.local_chains = cfg.n_chains // self.world
-        self.chain_offset = self.rank * self.local_chains
+        self.world, self.rank = par.world_info(group)
+        self.chain_offset, self.local_chains = par.shard_chains(cfg.n_chains, self.world, self.rank)
         if mode == "standard":
             self.op1 = self.op2 = self.op4 = self.op_target = None
         elif mode == "standard_Uphi":
@@ -119,8 +114,7 @@ class InfidelityStep:
         self.steps_done += 1
 
     def _allreduce(self, t):
-        if self.world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        par.allreduce_sum_(t, self.group)
 
     def estimate(self, psi, phi, return_grad=True):
         """Pass A (+ pass B).  Returns (sums[8] device tensor, L (S_local,), grad (P,) complex | None)."""

@@ -17,9 +17,8 @@ from .overlap_U.operator import InfidelityOperatorUPsi
 
 
 def _allreduce(t):
-    d = torch.distributed
-    if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
-        d.all_reduce(t, op=d.ReduceOp.SUM)
+    from ..parallel import allreduce_sum_
+    allreduce_sum_(t)
 
 
 def infidelity_expect(vstate: MCState, op, return_grad: bool):

@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing of the infidelity step (one process per GPU, torch.distributed).
+
+The path shards over Markov chains exactly like the reference's MPI scheme (NetKet
+`n_chains_per_rank`; gradient mean at infidelity/overlap/expect.py:126): rank r owns the global
+chains [r * n_local, (r+1) * n_local) of BOTH families.  Two sums cross the interconnect per step:
+
+  1. eight doubles  [sum L, sum L^2, sum |A|^2, sum Re A, n, 0, 0, 0]  after pass A, so that every rank
+     centres the score term with the GLOBAL mean F (what NetKet's mpi_statistics does);
+  2. the 2P-double gradient accumulator after pass B; then I_grad = -acc / n on every rank.
+
+Everything here is device-agnostic so that the algebra is testable with the gloo backend on CPUs
+(tests/test_multirank_gloo.py).
+"""
+
+from __future__ import annotations
+
+import torch
+
+
+def world_info(group=None):
+    d = torch.distributed
+    if d.is_available() and d.is_initialized():
+        return d.get_world_size(group), d.get_rank(group)
+    return 1, 0
+
+
+def shard_chains(n_chains_total: int, world: int, rank: int):
+    """(first global chain id, number of local chains) of `rank`."""
+    if n_chains_total % world:
+        raise ValueError(f"n_chains={n_chains_total} must be divisible by the number of ranks {world}")
+    n_local = n_chains_total // world
+    return rank * n_local, n_local
+
+
+def allreduce_sum_(t: torch.Tensor, group=None):
+    world, _ = world_info(group)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
+    return t
+
+
+def finalize_mean_var(sums):
+    """sums = [sum L, sum L^2, ., ., n, ...] (global) -> (F, variance)."""
+    n = float(sums[4])
+    F = float(sums[0]) / n
+    return F, max(0.0, float(sums[1]) / n - F * F)
+
+
+def finalize_grad(grad_acc: torch.Tensor, sums):
+    """I_grad = -acc / n  (infidelity/overlap/expect.py:126-127: mean over ranks, then negate)."""
+    return -grad_acc / float(sums[4])

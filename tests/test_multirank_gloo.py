@@ -1,0 +1,90 @@
+"""world_size-2 gloo test (CPU) of the multi-rank algebra of netket_fidelity_b200/parallel.py: each rank
+evaluates pass A / pass B on ITS shard of the sample pairs (the NumPy oracle stands in for the CUDA kernels),
+the two all-reduces combine them, and the result must equal the single-rank estimator and gradient.  Also
+checks the chain sharding used for the Philox chain ids."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import operators as oops
+from oracle.rbm import RBMParams, rbm_theta
+from oracle.infidelity import infidelity_and_grad, local_log_val, local_estimator
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _local_pass_B(psi, sigma, eta, A, L, F, cv, xp2, rho2):
+    """un-normalised accumulators sum_s [w_sig conj O(sigma) + w_eta conj D(eta)] in the flat layout."""
+    c = 0.0 if cv is None else cv
+    w_eta = np.conj(A) + 2 * c * np.abs(A) ** 2
+    w_sig = 2 * (L - F) - w_eta
+    ys = w_sig[:, None] * np.conj(np.tanh(rbm_theta(psi, sigma)))
+    S, C, N = xp2.shape
+    t_e = np.conj(np.tanh(rbm_theta(psi, xp2.reshape(-1, N)).reshape(S, C, -1)))
+    we = w_eta[:, None] * np.conj(rho2)
+    ye = we[:, :, None] * t_e
+    gW = sigma.T.astype(complex) @ ys + np.einsum("sci,scj->ij", xp2.astype(complex), ye)
+    gb = ys.sum(0) + ye.sum((0, 1))
+    ga = sigma.T.astype(complex) @ w_sig + np.einsum("sci,sc->i", xp2.astype(complex), we)
+    return np.concatenate([gb, gW.ravel(), ga])
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from netket_fidelity_b200 import parallel as par
+    N, S, n_chains = 4, 64, 8
+    psi, phi = RBMParams.random(N, 2, 1, std=0.2), RBMParams.random(N, 2, 2, std=0.2)
+    rng = np.random.default_rng(0)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    U, Ud, cv = oops.Rx(N, 1, 0.3), oops.Rx(N, 1, -0.3), -0.5
+    first, n_local = par.shard_chains(n_chains, world, rank)
+    assert (first, n_local) == (rank * 4, 4) and par.world_info() == (world, rank)
+    per_chain = S // n_chains
+    sl = slice(first * per_chain, (first + n_local) * per_chain)        # this rank's sample pairs
+    lv, xp2, rho2 = local_log_val(psi, phi, sigma[sl], eta[sl], U, Ud, None)
+    A, L = np.exp(lv), local_estimator(lv, cv)
+    sums = torch.tensor([L.sum(), (L ** 2).sum(), (np.abs(A) ** 2).sum(), A.real.sum(), len(L), 0, 0, 0],
+                        dtype=torch.float64)
+    par.allreduce_sum_(sums)                                             # collective 1
+    F, var = par.finalize_mean_var(sums)
+    acc = _local_pass_B(psi, sigma[sl], eta[sl], A, L, F, cv, xp2, rho2)
+    acc_t = torch.view_as_real(torch.tensor(acc)).contiguous()
+    par.allreduce_sum_(acc_t)                                            # collective 2
+    grad = par.finalize_grad(torch.view_as_complex(acc_t), sums).numpy()
+    ref = infidelity_and_grad(psi, phi, sigma, eta, cv, U, Ud, None)
+    ok = (abs(F - ref["F"]) < 1e-13 and abs(var - ref["L"].var()) < 1e-13
+          and np.allclose(grad, ref["grad"].ravel(), rtol=1e-11, atol=1e-14))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_reproduces_single_rank_result():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_chains_errors():
+    from netket_fidelity_b200 import parallel as par
+    assert par.shard_chains(16, 4, 3) == (12, 4)
+    with pytest.raises(ValueError):
+        par.shard_chains(10, 4, 0)
