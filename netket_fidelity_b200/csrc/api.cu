@@ -206,6 +206,7 @@ extern "C" int nkfb_create(int device, nkfb_handle_t *out) {
 extern "C" int nkfb_destroy(nkfb_handle_t h) {
   if (!h) return NKFB_ERR_INVALID;
   if (h->ws) cudaFree(h->ws);
+  if (h->ws2) cudaFree(h->ws2);
   delete h;
   return NKFB_OK;
 }

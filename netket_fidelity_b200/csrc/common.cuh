@@ -12,8 +12,10 @@ struct nkfb_handle_s {
   int sm_count;
   int64_t launches;
   char err[512];
-  void *ws;        // workspace of the *_host entry points
+  void *ws;        // scratch: gate matrix elements (nkfb_conn), sampler parameters when the caller gives none
   size_t ws_bytes;
+  void *ws2;       // scratch: bf16 splits of the RBM kernels for the tensor-core estimator / gradient
+  size_t ws2_bytes;
 };
 
 #define NKFB_CHECK_CUDA(h, call)                                                        \

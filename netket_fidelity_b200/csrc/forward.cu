@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 
 #include "tile.cuh"
 
@@ -510,6 +511,13 @@ extern "C" int nkfb_logpsi(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   return launch_logpsi<double, 4>(h, net, op, packed, B, local_states, out, st);
 }
 
+namespace nkfb {
+int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const nkfb_op_t *op1,
+                      const nkfb_op_t *op2, const nkfb_op_t *op4, const uint32_t *sigma, const uint32_t *eta,
+                      int64_t S, const double ls[2], double cv, void *log_val, void *L, void *rho1, double *sums,
+                      cudaStream_t st);
+}
+
 extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
                                    const nkfb_op_t *op1, const nkfb_op_t *op2, const nkfb_op_t *op4,
                                    const uint32_t *sigma, const uint32_t *eta, int64_t S,
@@ -529,6 +537,15 @@ extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const
   cudaStream_t st = (cudaStream_t)stream;
   const bool ising = (op1 && op1->kind == NKFB_OP_ISING) || (op2 && op2->kind == NKFB_OP_ISING) ||
                      (op4 && op4->kind == NKFB_OP_ISING);
+  {
+    // tensor-core path (fp32, NONE/GATE operators, large batches); NKFB_FWD_IMPL=simt forces the CUDA-core kernel
+    const char *impl = getenv("NKFB_FWD_IMPL");
+    if (!(impl && strcmp(impl, "simt") == 0)) {
+      rc = tc_infidelity_fwd(h, psi, phi, op1, op2, op4, sigma, eta, S, local_states, cv_coeff, log_val, L, rho1,
+                             sums, st);
+      if (rc <= 0) return rc;  // done (0) or error (< 0); 1 = not applicable
+    }
+  }
   if (psi->dtype == NKFB_F32)
     return ising ? launch_fwd<float, 4>(h, psi, phi, op1, op2, op4, sigma, eta, S, local_states, cv_coeff, log_val,
                                         L, rho1, sums, st)

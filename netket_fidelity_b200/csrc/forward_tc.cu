@@ -1,0 +1,533 @@
+// Tensor-core (tcgen05 + TMEM) version of pass A, the infidelity estimator, for fp32 parameters and
+// NONE / GATE operators (BASELINE configs C1, C2, C4).
+//
+//   Theta[s, f] = sum_k X[s, k] * W~[k, f]      s: 128 sample pairs (UMMA M = 128)
+//                                               k: spins + 1 bias row, padded to 16 (UMMA K = 16 per instruction)
+//                                               f: NN <= 256 real columns (Re/Im interleaved) per chunk (UMMA N)
+// X is exactly representable in bf16 (local states +-1 / 0,1); W~ is split into three bf16 terms
+// W~ = hi + mid + lo (3 x 8 mantissa bits = fp32), so three UMMAs per k-step accumulate an fp32-grade
+// product in TMEM.  Operands sit in shared memory in the canonical no-swizzle K-major layout
+// [k / 8][row][8] (16-byte core-matrix rows); the accumulator is read back with tcgen05.ld, one
+// thread per sample row, so the log-cosh row sums need no cross-thread reduction at all.
+//
+// log cosh z is accumulated in product form: sum_j (|x_j| - ln 2) + log prod_j (1 + t_j e^{-2 i y_j}),
+// t_j = e^{-2|x_j|}, i.e. MUFU.EX2 + MUFU.SIN + MUFU.COS per hidden unit and one complex log per 8 units;
+// the phase is therefore defined mod 2 pi (as any sum of principal-branch logs is, after exp()).
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include <cuda_bf16.h>
+
+#include "tile.cuh"
+
+namespace nkfb {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_ROWS = 128;  // sample pairs per tile (UMMA M)
+constexpr int TC_T = 2;       // tiles sharing one staged chunk of W~
+
+struct TcGeom {
+  int N, M, KT, KC, KS, NC, NN;  // KT = padded K, KC = KT/8 core chunks, KS = KT/16 k-steps, NC chunks of NN columns
+  __host__ __device__ size_t b_split_bytes() const { return (size_t)KC * NN * 16; }
+  __host__ __device__ size_t b_chunk_bytes() const { return 3 * b_split_bytes(); }
+  __host__ __device__ size_t a_bytes() const { return (size_t)KC * TC_ROWS * 16; }
+  __host__ __device__ size_t prep_bytes_per_net() const { return (size_t)NC * b_chunk_bytes(); }
+};
+
+static bool tc_geometry(int N, int M, TcGeom *g) {
+  g->N = N;
+  g->M = M;
+  g->KT = ((N + 1 + 15) / 16) * 16;
+  g->KC = g->KT / 8;
+  g->KS = g->KT / 16;
+  const int cols = 2 * M;
+  // columns per chunk: multiple of 16, <= 256, and 3 splits of the chunk + one X tile must fit in shared memory
+  const size_t budget = 200 * 1024 - (size_t)g->KC * TC_ROWS * 16 - 8192;
+  int nn_max = (int)std::min<size_t>(256, budget / ((size_t)3 * g->KC * 16));
+  nn_max = (nn_max / 16) * 16;
+  if (nn_max < 16) return false;
+  g->NC = (cols + nn_max - 1) / nn_max;
+  g->NN = (((cols + g->NC - 1) / g->NC) + 15) / 16 * 16;
+  return g->KT <= 1024;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // SmemDescriptor (sm_100): start address [0,14), leading byte offset [16,30), stride byte offset [32,46)
+  // (all >> 4), version = 1 at [46,48), base offset 0, layout type SWIZZLE_NONE = 0 at [61,64)
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int Mdim, int Ndim, int a_mn_major, int b_mn_major) {
+  // InstrDescriptor: c_format F32 = 1 at [4,6); a_format BF16 = 1 at [7,10); b_format BF16 = 1 at [10,13);
+  // a_major [15], b_major [16] (0 = K-major); n_dim = N >> 3 at [17,23); m_dim = M >> 4 at [24,29)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 8 consecutive fp32 columns of this thread's TMEM lane (row)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ operand preparation
+// Bprep[chunk][split][kc][n][8] bf16: element (k = 8 kc + e, n) of split `split` of W~, W~[k][col] with
+// col = chunk * NN + n: rows k < N from the kernel (N, M) complex interleaved, row N the bias, else 0.
+__global__ void tc_prep_kernel(NetDev<float> net, TcGeom g, __nv_bfloat16 *out) {
+  const int64_t total = (int64_t)g.NC * g.KC * g.NN;  // one thread per (chunk, kc, n): 8 k values x 3 splits
+  const int cols = 2 * g.M;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % g.NN);
+    const int kc = (int)((idx / g.NN) % g.KC);
+    const int chunk = (int)(idx / ((int64_t)g.NN * g.KC));
+    const int col = chunk * g.NN + n;
+    __align__(16) __nv_bfloat16 hi[8], mid[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      float w = 0.f;
+      if (col < cols) {
+        if (k < g.N)
+          w = net.W[(int64_t)k * cols + col];
+        else if (k == g.N && net.b)
+          w = net.b[col];
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      const float r1 = w - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(m);
+      hi[e] = h;
+      mid[e] = m;
+      lo[e] = __float2bfloat16_rn(r2);
+    }
+    const size_t split_elems = (size_t)g.KC * g.NN * 8;
+    __nv_bfloat16 *base = out + (size_t)chunk * 3 * split_elems + ((size_t)kc * g.NN + n) * 8;
+    *reinterpret_cast<uint4 *>(base) = *reinterpret_cast<const uint4 *>(hi);
+    *reinterpret_cast<uint4 *>(base + split_elems) = *reinterpret_cast<const uint4 *>(mid);
+    *reinterpret_cast<uint4 *>(base + 2 * split_elems) = *reinterpret_cast<const uint4 *>(lo);
+  }
+}
+
+// ------------------------------------------------------------------ log-cosh accumulation in product form
+struct LcAcc {
+  float sx, sy, lr, li;  // sum (|x| - ln 2), sum of the folded y, accumulated log of the flushed products
+  __device__ __forceinline__ void reset() { sx = sy = lr = li = 0.f; }
+  // multiply the running product (pr, pi) by 1 + t e^{-2iy}
+  __device__ __forceinline__ void add(float x, float y, float &pr, float &pi) {
+    if (x < 0.f) {
+      x = -x;
+      y = -y;
+    }
+    const float t = mufu_ex2(x * (float)(-2.0 * LOG2E));
+    const float a = 2.f * y;
+    const float c = mufu_cos(a), s = mufu_sin(a);
+    const float wr = fmaf(t, c, 1.f), wi = -t * s;
+    const float nr = pr * wr - pi * wi, ni = fmaf(pr, wi, pi * wr);
+    pr = nr;
+    pi = ni;
+    sx += x - (float)LN2;
+    sy += y;
+  }
+  __device__ __forceinline__ void flush(float &pr, float &pi) {
+    lr += 0.5f * (float)LN2 * mufu_lg2(fmaf(pr, pr, pi * pi));
+    li += atan2f(pi, pr);
+    pr = 1.f;
+    pi = 0.f;
+  }
+  __device__ __forceinline__ cx<float> value() const { return mk<float>(sx + lr, sy + li); }
+};
+
+struct TcFwdArgs {
+  OpDev op1, op2, op4;
+  const uint32_t *sigma, *eta;
+  int64_t S;
+  float s0, s1;
+  float cv;
+  int has_cv;
+  cx<float> *log_val;
+  float *L;
+  cx<float> *rho1;
+  double *sums;
+  const __nv_bfloat16 *prep_psi, *prep_phi;
+  TcGeom g;
+  int64_t n_groups;
+};
+
+// X tile in the canonical K-major no-swizzle layout [kc][row][8] bf16
+__device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_t *packed, int64_t s_base, int64_t S,
+                                                const TcGeom &g, float s0, float s1) {
+  const int W32 = (g.N + 31) >> 5;
+  const uint16_t b0 = __bfloat16_as_ushort(__float2bfloat16_rn(s0)), b1 = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
+  for (int idx = threadIdx.x; idx < g.KC * TC_ROWS; idx += TC_THREADS) {
+    const int kc = idx / TC_ROWS, r = idx - kc * TC_ROWS;
+    const int64_t gs = s_base + r;
+    uint32_t bits = 0;
+    const int k0 = kc * 8;
+    if (gs < S && k0 < g.N) bits = (packed[gs * W32 + (k0 >> 5)] >> (k0 & 31)) & 0xFFu;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t lo16 = 0, hi16 = 0;
+      const int ka = k0 + 2 * q, kb = ka + 1;
+      if (gs < S) {
+        lo16 = ka < g.N ? (((bits >> (2 * q)) & 1u) ? b1 : b0) : (ka == g.N ? 0x3F80u : 0u);
+        hi16 = kb < g.N ? (((bits >> (2 * q + 1)) & 1u) ? b1 : b0) : (kb == g.N ? 0x3F80u : 0u);
+      }
+      w[q] = lo16 | (hi16 << 16);
+    }
+    *reinterpret_cast<uint4 *>(As + (size_t)idx * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TcGeom g = a.g;
+  unsigned char *Bs = smem;                             // 3 splits of the current chunk
+  unsigned char *As = Bs + g.b_chunk_bytes();           // X tile
+  float *wg = reinterpret_cast<float *>(As + g.a_bytes());  // NN floats: row `idx` of W (this chunk) for the gate flip
+  cx<float> *xch = reinterpret_cast<cx<float> *>(wg + g.NN);  // exchange buffer [7][TC_ROWS]
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ double red[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane;  // TMEM lane == sample row of the tile
+  const int half = warp >> 2;              // which half of the chunk's columns this thread reduces
+  const uint32_t mbar_a = smem_u32(&mbar);
+
+  if (tid == 0) {
+    mbar_init(mbar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_sh;
+  const uint32_t idesc = umma_idesc_bf16_f32(TC_ROWS, g.NN, 0, 0);
+  uint32_t parity = 0;
+
+  const float ssum = a.s0 + a.s1;
+  const int W32 = (g.N + 31) >> 5;
+  const int cols = 2 * g.M;
+  double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0;
+
+  for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    // accumulators: [tile][eval] with eval 0 = (psi,sigma) 1 = (psi,eta) 2 = (phi,sigma) 3 = (phi,eta); flips for 1,2,3
+    LcAcc acc0[TC_T][4], acc1[TC_T][4];
+#pragma unroll
+    for (int t = 0; t < TC_T; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc0[t][e].reset();
+        acc1[t][e].reset();
+      }
+
+#pragma unroll
+    for (int netid = 0; netid < 2; ++netid) {
+      const NetDev<float> &net = netid == 0 ? psi : phi;
+      const __nv_bfloat16 *prep = netid == 0 ? a.prep_psi : a.prep_phi;
+#pragma unroll 1
+      for (int chunk = 0; chunk < g.NC; ++chunk) {
+        __syncthreads();  // everyone is done with the previous chunk's Bs / wg
+        {                 // stage the three bf16 splits of this chunk
+          const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(prep) +
+                                                             (size_t)chunk * g.b_chunk_bytes());
+          uint4 *dst = reinterpret_cast<uint4 *>(Bs);
+          const int n16 = (int)(g.b_chunk_bytes() / 16);
+          for (int i = tid; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int t = 0; t < TC_T; ++t) {
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const int ev = netid * 2 + side;
+            const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+            const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
+            const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+            const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+            if (flip) {
+              for (int n = tid; n < g.NN; n += TC_THREADS) {
+                const int col = chunk * g.NN + n;
+                wg[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
+              }
+            }
+            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+              tc_fence_after();
+              const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+              for (int s = 0; s < 3; ++s)
+                for (int ks = 0; ks < g.KS; ++ks) {
+                  const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                  const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (g.NN * 16),
+                                                g.NN * 16, 128);
+                  umma_bf16(tmem_d, ad, bd, idesc, (s | ks) ? 1u : 0u);
+                }
+              umma_commit(mbar_a);
+            }
+            mbar_wait(mbar_a, parity);
+            parity ^= 1;
+            tc_fence_after();
+            // ---- epilogue: this thread's row, its half of the chunk's columns
+            float d = 0.f;
+            if (flip) {
+              const int64_t gs = s_base + row;
+              if (gs < a.S) {
+                const uint32_t w = packed[gs * W32 + (op.idx >> 5)];
+                d = ssum - 2.f * (((w >> (op.idx & 31)) & 1u) ? a.s1 : a.s0);
+              }
+            }
+            LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
+            const int nh = g.NN / 2;  // columns per half (multiple of 8)
+            const uint32_t trow = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16);
+            int cnt = 0;
+            float p0r = 1.f, p0i = 0.f, p1r = 1.f, p1i = 0.f;
+#pragma unroll 1
+            for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
+              float v[8];
+              tmem_ld8(trow + (uint32_t)c0, v);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int col = chunk * g.NN + c0 + 2 * u;
+                if (col < cols) {
+                  A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
+                  if (flip)
+                    A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
+                }
+              }
+              if ((++cnt & 1) == 0) {
+                A0.flush(p0r, p0i);
+                if (flip) A1.flush(p1r, p1i);
+              }
+            }
+            if (cnt & 1) {
+              A0.flush(p0r, p0i);
+              if (flip) A1.flush(p1r, p1i);
+            }
+            tc_fence_before();
+            __syncthreads();  // TMEM, As and wg may be overwritten now
+          }
+        }
+      }
+    }
+
+    // ---- combine the two column halves, add the visible-bias terms, finish the estimator
+#pragma unroll
+    for (int t = 0; t < TC_T; ++t) {
+      const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+      __syncthreads();
+      if (half == 1) {
+        xch[0 * TC_ROWS + row] = acc0[t][0].value();
+        xch[1 * TC_ROWS + row] = acc0[t][1].value();
+        xch[2 * TC_ROWS + row] = acc0[t][2].value();
+        xch[3 * TC_ROWS + row] = acc0[t][3].value();
+        xch[4 * TC_ROWS + row] = acc1[t][1].value();
+        xch[5 * TC_ROWS + row] = acc1[t][2].value();
+        xch[6 * TC_ROWS + row] = acc1[t][3].value();
+      }
+      __syncthreads();
+      const int64_t gs = s_base + row;
+      if (half == 0 && gs < a.S) {
+        cx<float> b0[4], b1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b0[e] = acc0[t][e].value() + xch[e * TC_ROWS + row];
+        b1[0] = mk<float>(0, 0);
+#pragma unroll
+        for (int e = 1; e < 4; ++e) b1[e] = acc1[t][e].value() + xch[(3 + e) * TC_ROWS + row];
+        // visible-bias terms a.x for (psi, sigma) (psi, eta) (phi, sigma) (phi, eta)
+        cx<float> ax[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)};
+        for (int i = 0; i < g.N; ++i) {
+          const float xs = ((a.sigma[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+          const float xe = ((a.eta[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+          if (psi.a) {
+            const cx<float> ai = mk<float>(psi.a[2 * i], psi.a[2 * i + 1]);
+            ax[0] = ax[0] + xs * ai;
+            ax[1] = ax[1] + xe * ai;
+          }
+          if (phi.a) {
+            const cx<float> ai = mk<float>(phi.a[2 * i], phi.a[2 * i + 1]);
+            ax[2] = ax[2] + xs * ai;
+            ax[3] = ax[3] + xe * ai;
+          }
+        }
+        cx<float> T[4], rho = mk<float>(0, 0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const OpDev &op = (e == 1) ? a.op2 : (e == 2 ? a.op1 : a.op4);
+          const NetDev<float> &net = e < 2 ? psi : phi;
+          const uint32_t *packed = (e & 1) ? a.eta : a.sigma;
+          const cx<float> l0 = b0[e] + ax[e];
+          if (e == 0 || op.kind != NKFB_OP_GATE) {
+            T[e] = l0;
+          } else {
+            const int bit = (packed[gs * W32 + (op.idx >> 5)] >> (op.idx & 31)) & 1u;
+            const float dd = ssum - 2.f * (bit ? a.s1 : a.s0);
+            cx<float> l1 = b1[e] + ax[e];
+            if (net.a) l1 = l1 + dd * mk<float>(net.a[2 * op.idx], net.a[2 * op.idx + 1]);
+            const cx<float> m0 = mk<float>((float)op.gate_mel[bit][0][0], (float)op.gate_mel[bit][0][1]);
+            const cx<float> m1 = mk<float>((float)op.gate_mel[bit][1][0], (float)op.gate_mel[bit][1][1]);
+            const float amax = fmaxf(l0.re, l1.re);
+            const cx<float> e0 = m0 * cexp(mk<float>(l0.re - amax, l0.im));
+            const cx<float> e1 = m1 * cexp(mk<float>(l1.re - amax, l1.im));
+            const cx<float> sum = e0 + e1;
+            T[e] = clog(sum);
+            T[e].re += amax;
+            if (e == 1) rho = (1.f / abs2(sum)) * (e1 * conj(sum));
+          }
+        }
+        // l = T(phi,sigma) + T(psi,eta) - T(psi,sigma) - T(phi,eta)
+        const cx<float> l = T[2] + T[1] - T[0] - T[3];
+        const cx<float> A = cexp(l);
+        const float A2 = abs2(A);
+        float Lv = A.re;
+        if (a.has_cv) Lv += a.cv * (A2 - 1.f);
+        a.log_val[gs] = l;
+        a.L[gs] = Lv;
+        a.rho1[gs] = rho;
+        sL += (double)Lv;
+        sL2 += (double)Lv * (double)Lv;
+        sA2 += (double)A2;
+        sRe += (double)A.re;
+        sn += 1.0;
+      }
+    }
+  }
+
+  double v[5] = {sL, sL2, sA2, sRe, sn};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    double r = block_sum_256(v[q], red);
+    if (threadIdx.x == 0) atomicAdd(a.sums + q, r);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+static bool bf16_exact(double v) {
+  const float f = (float)v;
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (double)f == v && (u & 0xFFFFu) == 0;
+}
+
+// returns NKFB_OK, an error, or 1 when the tensor-core path does not apply (caller falls back to the SIMT kernel)
+int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const nkfb_op_t *op1,
+                      const nkfb_op_t *op2, const nkfb_op_t *op4, const uint32_t *sigma, const uint32_t *eta,
+                      int64_t S, const double ls[2], double cv, void *log_val, void *L, void *rho1, double *sums,
+                      cudaStream_t st) {
+  if (psi->dtype != NKFB_F32) return 1;
+  const nkfb_op_t *ops[3] = {op1, op2, op4};
+  for (int i = 0; i < 3; ++i)
+    if (ops[i] && ops[i]->kind == NKFB_OP_ISING) return 1;
+  if (psi->n_hidden != phi->n_hidden) return 1;
+  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
+  if (S < 2048) return 1;
+  TcGeom g;
+  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g)) return 1;
+  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + (size_t)g.NN * 4 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
+  if (smem > 227 * 1024) return 1;
+
+  // prepared bf16 splits of both networks live in the handle's second workspace
+  const size_t need = 2 * g.prep_bytes_per_net();
+  if (h->ws2_bytes < need) {
+    if (h->ws2) cudaFree(h->ws2);
+    h->ws2 = nullptr;
+    h->ws2_bytes = 0;
+    NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws2, need));
+    h->ws2_bytes = need;
+  }
+  __nv_bfloat16 *prep_psi = (__nv_bfloat16 *)h->ws2;
+  __nv_bfloat16 *prep_phi = (__nv_bfloat16 *)((char *)h->ws2 + g.prep_bytes_per_net());
+  {
+    const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
+    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, prep_psi);
+    NKFB_LAUNCHED(h);
+    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(phi), g, prep_phi);
+    NKFB_LAUNCHED(h);
+  }
+  TcFwdArgs a;
+  a.op1 = make_opdev(op1);
+  a.op2 = make_opdev(op2);
+  a.op4 = make_opdev(op4);
+  a.sigma = sigma;
+  a.eta = eta;
+  a.S = S;
+  a.s0 = (float)ls[0];
+  a.s1 = (float)ls[1];
+  a.has_cv = !isnan(cv);
+  a.cv = a.has_cv ? (float)cv : 0.f;
+  a.log_val = (cx<float> *)log_val;
+  a.L = (float *)L;
+  a.rho1 = (cx<float> *)rho1;
+  a.sums = sums;
+  a.prep_psi = prep_psi;
+  a.prep_phi = prep_phi;
+  a.g = g;
+  const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
+  a.n_groups = (tiles + TC_T - 1) / TC_T;
+  NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count);
+  infid_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+}  // namespace nkfb

@@ -1,0 +1,60 @@
+"""Tensor-core (tcgen05) estimator / gradient kernels against the CPU oracle and against the CUDA-core kernels
+(fp32; tolerance 1e-5 relative as stated in BASELINE.json's north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import operators as oops
+from oracle.rbm import RBMParams
+from oracle.infidelity import infidelity_and_grad, mode_slots
+from tests._helpers import to_rbmspec, to_opspec, pack_np, packed_to_torch, rel_err
+
+pytestmark = pytest.mark.gpu
+LS = (-1.0, 1.0)
+
+
+@pytest.fixture(scope="module")
+def h():
+    from netket_fidelity_b200._native import get_handle
+    return get_handle(0)
+
+
+def _net(N, M, seed, std):
+    p = RBMParams.random(N, -(-M // N), seed, std=std)
+    return RBMParams(p.kernel[:, :M].copy(), p.bias[:M].copy(), p.visible_bias)
+
+
+@pytest.mark.parametrize("N,M,S,std", [(4, 4, 2500, 0.2), (20, 40, 4096, 0.05), (33, 70, 2100, 0.05),
+                                        (100, 400, 4096, 0.01), (64, 128, 3000, 0.02)])
+@pytest.mark.parametrize("cv", [None, -0.5])
+def test_tc_estimator_and_gradient(h, N, M, S, std, cv):
+    rng = np.random.default_rng(7)
+    psi, phi = _net(N, M, 1234, std), _net(N, M, 5678, std)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    a, b = to_rbmspec(psi, torch.complex64), to_rbmspec(phi, torch.complex64)
+    modes = [("standard", None, None), ("upsi", oops.Rx(N, N // 2, 0.37), oops.Rx(N, N // 2, -0.37)),
+             ("upsi", oops.Hadamard(N, N - 1), oops.Hadamard(N, N - 1)), ("standard_Uphi", oops.Ry(N, 0, 0.3), None)]
+    for mode, U, Ud in modes:
+        U1, U2, U4 = mode_slots(mode, U, Ud)
+        ref = infidelity_and_grad(psi, phi, sigma, eta, cv, U1, U2, U4)
+        out = {}
+        for impl in ("tc", "simt"):
+            os.environ["NKFB_FWD_IMPL"] = impl
+            os.environ["NKFB_GRAD_IMPL"] = impl
+            lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, cv, to_opspec(U1), to_opspec(U2), to_opspec(U4))
+            gacc = h.infidelity_grad(a, sp, ep, LS, cv, lv, rho1, sums, to_opspec(U2))
+            g = h.grad_finalize(gacc, sums, a.n_params, torch.complex64).cpu().numpy()
+            torch.cuda.synchronize()
+            s = sums.cpu().numpy()
+            out[impl] = (L.cpu().numpy(), s, g, rho1.cpu().numpy())
+            assert s[4] == S
+            assert rel_err(out[impl][0], ref["L"]) <= 1e-4, (impl, mode, U)
+            assert abs(s[0] / S - ref["F"]) <= 1e-5 * max(1.0, abs(ref["F"])), (impl, mode, U)
+            assert rel_err(g, ref["grad"].ravel()) <= 2e-4, (impl, mode, U, rel_err(g, ref["grad"].ravel()))
+        os.environ.pop("NKFB_FWD_IMPL")
+        os.environ.pop("NKFB_GRAD_IMPL")
+        # the two implementations must also agree with each other on the per-sample estimator
+        assert rel_err(out["tc"][0], out["simt"][0]) <= 1e-4
