@@ -207,6 +207,7 @@ extern "C" int nkfb_destroy(nkfb_handle_t h) {
   if (!h) return NKFB_ERR_INVALID;
   if (h->ws) cudaFree(h->ws);
   if (h->ws2) cudaFree(h->ws2);
+  if (h->ws3) cudaFree(h->ws3);
   delete h;
   return NKFB_OK;
 }

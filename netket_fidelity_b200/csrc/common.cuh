@@ -14,8 +14,10 @@ struct nkfb_handle_s {
   char err[512];
   void *ws;        // scratch: gate matrix elements (nkfb_conn), sampler parameters when the caller gives none
   size_t ws_bytes;
-  void *ws2;       // scratch: bf16 splits of the RBM kernels for the tensor-core estimator / gradient
+  void *ws2;       // scratch: bf16 splits of the RBM kernels for the tensor-core estimator
   size_t ws2_bytes;
+  void *ws3;       // scratch: bf16 splits of the RBM kernel for the tensor-core gradient
+  size_t ws3_bytes;
 };
 
 #define NKFB_CHECK_CUDA(h, call)                                                        \

@@ -516,6 +516,9 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
                       const nkfb_op_t *op2, const nkfb_op_t *op4, const uint32_t *sigma, const uint32_t *eta,
                       int64_t S, const double ls[2], double cv, void *log_val, void *L, void *rho1, double *sums,
                       cudaStream_t st);
+int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
+                       const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st);
 }
 
 extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
@@ -571,6 +574,13 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
   if (S <= 0) return NKFB_OK;
   if (!sigma || !eta || !log_val || !rho1 || !sums || !grad_acc) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const char *impl = getenv("NKFB_GRAD_IMPL");
+    if (!(impl && strcmp(impl, "simt") == 0)) {
+      rc = tc_infidelity_grad(h, psi, op2, sigma, eta, S, local_states, cv_coeff, log_val, rho1, sums, grad_acc, st);
+      if (rc <= 0) return rc;
+    }
+  }
   if (psi->dtype == NKFB_F32)
     return launch_grad<float, 8>(h, psi, op2, sigma, eta, S, local_states, cv_coeff, log_val, rho1, sums, grad_acc,
                                  st);

@@ -1,0 +1,334 @@
+// Tensor-core (tcgen05 + TMEM) version of pass B, the score-function gradient, for fp32 parameters and
+// NONE / GATE operators.  A CTA owns one chunk of NN real columns of the (N+1) x 2(M+1) gradient tile
+// [rows: spins + bias row; columns: hidden units Re/Im + one pseudo-unit for the visible bias] and a range of
+// sample tiles.  Per tile and side (sigma, eta):
+//   GEMM 1  Theta[s, f]  = X[s, :] W~[:, f]            UMMA 128 x NN x 16, A = X tile (K-major), bf16 x 3 splits
+//   epilogue             Y[s, f] = w_s conj(tanh Theta[s, f])  (+ the flipped connected element for a gate)
+//                        one thread per sample row, written back to shared memory as three bf16 splits
+//   GEMM 2  G[i, f]     += X[s, i] Y[s, f]             UMMA 128 x NN x 16, A = the SAME X tile read MN-major
+//                                                      (rows = spins), B = Y MN-major; G stays in TMEM
+// and at the end G is read from TMEM and added to the fp64 accumulators with one atomic per element.
+#include "tc_common.cuh"
+
+namespace nkfb {
+
+constexpr int GX_CHUNKS = 16;  // the X tile always spans 128 "spin rows" (UMMA M of GEMM 2), zero padded
+
+struct TcGradArgs {
+  OpDev op2;
+  const uint32_t *sigma, *eta;
+  int64_t S;
+  float s0, s1, cv;
+  int has_cv;
+  const cx<float> *log_val, *rho1;
+  const double *sums;
+  double *grad_acc;
+  const __nv_bfloat16 *prep;
+  TcGeom g;
+  int64_t tiles_per_split;
+  int has_bias, has_vbias;
+};
+
+// tanh z with MUFU: sg ((1 - t^2) + 2 i t sin 2y) / (1 + 2 t cos 2y + t^2), t = e^{-2|x|}
+__device__ __forceinline__ cx<float> ctanh_fast(float x, float y) {
+  float sg = 1.f;
+  if (x < 0.f) {
+    x = -x;
+    y = -y;
+    sg = -1.f;
+  }
+  const float t = mufu_ex2(x * (float)(-2.0 * LOG2E));
+  const float a = 2.f * y;
+  const float c = mufu_cos(a), s = mufu_sin(a);
+  const float inv = __fdividef(sg, fmaf(t, fmaf(2.f, c, t), 1.f));
+  return mk<float>((1.f - t * t) * inv, 2.f * t * s * inv);
+}
+
+__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float ra = a - __low2float(h), rb = b - __high2float(h);
+  const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+  const float qa = ra - __low2float(m), qb = rb - __high2float(m);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(qa, qb);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  mid = *reinterpret_cast<const uint32_t *>(&m);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<float> psi, TcGradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TcGeom g = a.g;
+  const int NN = g.NN;
+  const size_t y_split_bytes = (size_t)(NN / 8) * TC_ROWS * 16;
+  unsigned char *Bs = smem;                                      // W~ chunk, 3 splits, resident
+  unsigned char *As = Bs + g.b_chunk_bytes();                    // X tile [16][128][8] bf16
+  unsigned char *Ys = As + (size_t)GX_CHUNKS * TC_ROWS * 16;     // Y tile, 3 splits of [NN/8][128][8] bf16
+  float *wg = reinterpret_cast<float *>(Ys + 3 * y_split_bytes);  // NN: row idx of W (gate flip)
+  float *corr = wg + NN;                                         // NN: correction of row idx
+  cx<float> *wts = reinterpret_cast<cx<float> *>(corr + NN);     // [3][128]: w_sig, w_eta, conj(rho1)
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane;
+  const int half = warp >> 2;
+  const uint32_t mbar_a = smem_u32(&mbar);
+  const int chunk = blockIdx.x;
+  const int N = g.N, M = g.M, cols = 2 * M;
+  const int W32 = (N + 31) >> 5;
+  const bool gate = a.op2.kind == NKFB_OP_GATE;
+  const int gidx = a.op2.idx;
+  const float ssum = a.s0 + a.s1;
+  const double F = a.sums[0] / a.sums[4];
+  const float cvc = a.has_cv ? a.cv : 0.f;
+
+  if (tid == 0) {
+    mbar_init(mbar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), 512);
+  {  // stage the chunk of W~ (resident for the whole kernel), the gate row, zero the correction
+    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(a.prep) +
+                                                       (size_t)chunk * g.b_chunk_bytes());
+    uint4 *dst = reinterpret_cast<uint4 *>(Bs);
+    const int n16 = (int)(g.b_chunk_bytes() / 16);
+    for (int i = tid; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (int n = tid; n < NN; n += TC_THREADS) {
+      const int col = chunk * NN + n;
+      wg[n] = (gate && col < cols) ? psi.W[(int64_t)gidx * cols + col] : 0.f;
+      corr[n] = 0.f;
+    }
+    // rows >= KC*8 of the X tile (beyond the padded spin count) stay zero for the whole kernel
+    uint4 *az = reinterpret_cast<uint4 *>(As);
+    for (int i = tid; i < GX_CHUNKS * TC_ROWS; i += TC_THREADS) az[i] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_theta = tmem_base_sh;        // NN columns
+  const uint32_t tmem_g = tmem_base_sh + 256;      // NN columns, persistent
+  const uint32_t idesc1 = umma_idesc_bf16_f32(TC_ROWS, NN, 0, 0);
+  const uint32_t idesc2 = umma_idesc_bf16_f32(TC_ROWS, NN, 1, 1);
+  uint32_t parity = 0;
+  bool g_started = false;
+
+  const int64_t n_tiles = (a.S + TC_ROWS - 1) / TC_ROWS;
+  const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
+  const int64_t t_end = min(n_tiles, t_begin + a.tiles_per_split);
+  const int nh = NN / 2;
+  const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const int64_t s_base = tile * TC_ROWS;
+    // per-sample weights: w_eta = conj(A) + 2 c |A|^2, w_sig = 2 (L - F) - w_eta
+    if (tid < TC_ROWS) {
+      const int64_t gs = s_base + tid;
+      cx<float> ws_ = mk<float>(0, 0), we_ = mk<float>(0, 0), rh_ = mk<float>(0, 0);
+      if (gs < a.S) {
+        const cx<float> A = cexp(a.log_val[gs]);
+        const float A2 = abs2(A);
+        const float Lv = A.re + cvc * (A2 - 1.f);
+        we_ = mk<float>(A.re + 2.f * cvc * A2, -A.im);
+        const float dl = (float)(2.0 * ((double)Lv - F));
+        ws_ = mk<float>(dl - we_.re, -we_.im);
+        rh_ = conj(a.rho1[gs]);
+      }
+      wts[tid] = ws_;
+      wts[TC_ROWS + tid] = we_;
+      wts[2 * TC_ROWS + tid] = rh_;
+    }
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+      const bool flip = gate && side == 1;
+      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {  // GEMM 1: Theta = X W~
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+        for (int s = 0; s < 3; ++s)
+          for (int ks = 0; ks < g.KS; ++ks) {
+            const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+            const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (NN * 16), NN * 16, 128);
+            umma_bf16(tmem_theta, ad, bd, idesc1, (s | ks) ? 1u : 0u);
+          }
+        umma_commit(mbar_a);
+      }
+      mbar_wait(mbar_a, parity);
+      parity ^= 1;
+      tc_fence_after();
+      // ---- epilogue: Y[s, f] for this thread's row and its half of the columns
+      const cx<float> w = side == 0 ? wts[row] : wts[TC_ROWS + row];
+      const cx<float> r1 = flip ? wts[2 * TC_ROWS + row] : mk<float>(0, 0);  // conj(rho_1)
+      const cx<float> r0 = mk<float>(1.f - r1.re, -r1.im);                    // conj(rho_0)
+      float d = 0.f;
+      if (flip) {
+        const int64_t gs = s_base + row;
+        if (gs < a.S) {
+          const uint32_t wd = packed[gs * W32 + (gidx >> 5)];
+          d = ssum - 2.f * (((wd >> (gidx & 31)) & 1u) ? a.s1 : a.s0);
+        }
+      }
+#pragma unroll 1
+      for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
+        float v[8], y[8], cc[8];
+        tmem_ld8(tmem_theta + lane_off + (uint32_t)c0, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = (chunk * NN + c0) / 2 + u;  // hidden-unit index of this complex column
+          cx<float> out = mk<float>(0, 0), c1 = mk<float>(0, 0);
+          if (j <= M) {
+            cx<float> t0 = mk<float>(1, 0), t1 = mk<float>(1, 0);  // pseudo-unit j == M: O_{a_i} = x_i
+            if (j < M) {
+              t0 = conj(ctanh_fast(v[2 * u], v[2 * u + 1]));
+              if (flip)
+                t1 = conj(ctanh_fast(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1])));
+            }
+            if (flip) {
+              c1 = w * (r1 * t1);
+              out = w * (r0 * t0) + c1;
+            } else {
+              out = w * t0;
+            }
+          }
+          y[2 * u] = out.re;
+          y[2 * u + 1] = out.im;
+          cc[2 * u] = d * c1.re;
+          cc[2 * u + 1] = d * c1.im;
+        }
+        // three bf16 splits of the 8 columns -> [c0/8][row][8] (MN-major B operand of GEMM 2)
+        uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split3(y[2 * q], y[2 * q + 1], hi[q], mid[q], lo[q]);
+        unsigned char *dst = Ys + ((size_t)(c0 / 8) * TC_ROWS + row) * 16;
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(dst + y_split_bytes) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+        *reinterpret_cast<uint4 *>(dst + 2 * y_split_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (flip) {  // correction of row idx: sum over the samples of d_s w_eta conj(rho_1) conj(tanh theta')
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float r = cc[q];
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+            if (lane == 0) atomicAdd(corr + c0 + q, r);
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {  // GEMM 2: G += X^T Y
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(As), y_base = smem_u32(Ys);
+        for (int s = 0; s < 3; ++s)
+          for (int ks = 0; ks < TC_ROWS / 16; ++ks) {
+            // A: X tile read MN-major (rows = spins): 8-spin groups 2048 B apart (SBO), 8-sample groups 128 B apart (LBO)
+            const uint64_t ad = umma_desc(a_base + ks * 256, 128, TC_ROWS * 16);
+            // B: Y MN-major: 8-column groups 2048 B apart (SBO), 8-sample groups 128 B apart (LBO)
+            const uint64_t bd = umma_desc(y_base + s * (uint32_t)y_split_bytes + ks * 256, 128, TC_ROWS * 16);
+            umma_bf16(tmem_g, ad, bd, idesc2, (g_started || s || ks) ? 1u : 0u);
+          }
+        umma_commit(mbar_a);
+      }
+      g_started = true;
+      mbar_wait(mbar_a, parity);
+      parity ^= 1;
+      tc_fence_after();
+    }
+  }
+
+  // ---- flush G (TMEM lane = gradient row: spins, then the bias row N) to the fp64 accumulators
+  __syncthreads();
+  if (g_started) {
+    const int i = row;
+    const int64_t offK = 2 * (int64_t)M, offA = 2 * ((int64_t)M + (int64_t)N * M);
+    for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem_g + lane_off + (uint32_t)c0, v);
+      if (i <= N) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = chunk * NN + c0 + q;
+          const int j = col >> 1, comp = col & 1;
+          float val = v[q];
+          if (gate && i == gidx) val += corr[c0 + q];
+          if (j < M) {
+            if (i < N)
+              atomicAdd(a.grad_acc + offK + 2 * ((int64_t)i * M + j) + comp, (double)val);
+            else if (a.has_bias)
+              atomicAdd(a.grad_acc + 2 * j + comp, (double)val);
+          } else if (j == M && i < N && a.has_vbias) {
+            atomicAdd(a.grad_acc + offA + 2 * i + comp, (double)val);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_sh, 512);
+}
+
+// returns NKFB_OK, an error, or 1 when the tensor-core path does not apply
+int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
+                       const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st) {
+  if (psi->dtype != NKFB_F32) return 1;
+  if (op2 && op2->kind == NKFB_OP_ISING) return 1;
+  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
+  if (S < 2048) return 1;
+  const int N = psi->n_visible, M = psi->n_hidden;
+  if (N + 1 > TC_ROWS) return 1;  // GEMM 2 holds all gradient rows (spins + bias) in one UMMA M = 128 tile
+  TcGeom g;
+  // per column: three bf16 splits of a 128-sample Y tile (768 B) + gate row + correction (8 B)
+  if (!tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16)) return 1;
+  const size_t y_bytes = 3 * (size_t)(g.NN / 8) * TC_ROWS * 16;
+  const size_t smem = g.b_chunk_bytes() + (size_t)GX_CHUNKS * TC_ROWS * 16 + y_bytes + 2 * (size_t)g.NN * 4 +
+                      3 * TC_ROWS * sizeof(cx<float>) + 128;
+  if (smem > 227 * 1024) return 1;
+
+  const size_t need = g.prep_bytes_per_net();
+  if (h->ws3_bytes < need) {
+    if (h->ws3) cudaFree(h->ws3);
+    h->ws3 = nullptr;
+    h->ws3_bytes = 0;
+    NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws3, need));
+    h->ws3_bytes = need;
+  }
+  {
+    const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
+    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, (__nv_bfloat16 *)h->ws3);
+    NKFB_LAUNCHED(h);
+  }
+  TcGradArgs a;
+  a.op2 = make_opdev(op2);
+  a.sigma = sigma;
+  a.eta = eta;
+  a.S = S;
+  a.s0 = (float)ls[0];
+  a.s1 = (float)ls[1];
+  a.has_cv = !isnan(cv);
+  a.cv = a.has_cv ? (float)cv : 0.f;
+  a.log_val = (const cx<float> *)log_val;
+  a.rho1 = (const cx<float> *)rho1;
+  a.sums = sums;
+  a.grad_acc = grad_acc;
+  a.prep = (const __nv_bfloat16 *)h->ws3;
+  a.g = g;
+  a.has_bias = psi->bias != nullptr;
+  a.has_vbias = psi->visible_bias != nullptr;
+  const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
+  int64_t n_splits = std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)h->sm_count / g.NC));
+  a.tiles_per_split = (tiles + n_splits - 1) / n_splits;
+  n_splits = (tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(g.NC, (unsigned)n_splits);
+  infid_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+}  // namespace nkfb
