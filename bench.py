@@ -118,6 +118,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def host_ops(w, hi):
+    import netket_fidelity_b200 as nkf
+    from netket_fidelity_b200 import nk
+    u = w["U"]
+    if u[0] == "rx":
+        return nkf.operator.Rx(hi, u[1], u[2]), nkf.operator.Rx(hi, u[1], -u[2])
+    if u[0] == "hadamard":
+        return nkf.operator.Hadamard(hi, u[1]), nkf.operator.Hadamard(hi, u[1])
+    if u[0] == "ising_prop":
+        return nkf.operator.IsingPropagator(hi, nk.graph.Chain(w["N"]), u[2], u[3], u[1]), None
+    raise ValueError(u)
+
+
 def bench_config(name, w, n_gpus):
     return {"workload": f"{name}: N={w['N']} spins, RBM alpha={w['M'] // w['N']} complex (M={w['M']}), "
                         f"{w['n_chains'] * w['chain_length']} sample pairs = {w['n_chains']} chains x "
@@ -175,6 +188,7 @@ def run_b200(args):
     if rank == 0:
         clocks.start()
     samp_ev = [(ev(), ev()) for _ in range(args.steps)]
+    est_ev = [(ev(), ev(), ev()) for _ in range(args.steps)]
     launches0 = h.launches
     barrier()
     e0, e1 = ev(), ev()
@@ -184,7 +198,7 @@ def run_b200(args):
         samp_ev[i][0].record()
         eng.sample(specs["psi"], specs["phi"])
         samp_ev[i][1].record()
-        sums, L, grad = eng.estimate(specs["psi"], specs["phi"])
+        sums, L, grad = eng.estimate(specs["psi"], specs["phi"], events=est_ev[i])
     e1.record()
     barrier()
     launches = h.launches - launches0
@@ -195,21 +209,47 @@ def run_b200(args):
     ms_total = float(t.item())
     clk = clocks.stop() if rank == 0 else None
     samp_ms = sum(a.elapsed_time(b) for a, b in samp_ev) / args.steps   # two sampler launches per step
+    fwd_ms = sum(a.elapsed_time(b) for a, b, c in est_ev) / args.steps
+    grad_ms = sum(b.elapsed_time(c) for a, b, c in est_ev) / args.steps  # includes the 64-byte all-reduce when N > 1
     s = sums.cpu().numpy()
     infid = 1.0 - s[0] / s[4]
 
-    # ------------------------------------------------------------ end-to-end (host buffers)
+    # ------------------------------------------------------------ end-to-end through the public API (host buffers)
+    # psi.parameters <- pinned host copy (H2D), reset both states, psi.expect_and_grad(I_op) [sampling of both
+    # families + estimator + gradient + all-reduces], gradient and statistics back to pinned host memory (D2H).
+    import netket_fidelity_b200 as nkf
+    from netket_fidelity_b200 import nk
+    hi = nk.hilbert.Spin(0.5, N)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=w["n_chains"], sweep_size=N)
+    ma = nk.models.RBM(alpha=M // N, param_dtype=(complex if args.dtype == "f64" else "complex64"),
+                       use_visible_bias=w["vb"])
+    S_total = w["n_chains"] * w["chain_length"]
+    mk_tree = lambda t: {"Dense": {"kernel": t[0], "bias": t[1]}, **({"visible_bias": t[2]} if t[2] is not None else {})}
+    vs_psi = nk.vqs.MCState(sa, ma, n_samples=S_total, n_discard_per_chain=5, seed=1, device=dev,
+                            variables={"params": mk_tree(devp["psi"])})
+    vs_phi = nk.vqs.MCState(sa, ma, n_samples=S_total, n_discard_per_chain=5, seed=2, device=dev,
+                            variables={"params": mk_tree(devp["phi"])})
+    Uop, Udop = host_ops(w, hi)
+    I_op = nkf.InfidelityOperator(vs_phi, U=Uop, U_dagger=Udop, cv_coeff=-0.5,
+                                  is_unitary=(w["mode"] == "upsi"), sample_Upsi=(w["mode"] == "standard_Uphi"))
+    pin_tree = {k: mk_tree(pinned[k]) for k in pinned}
+
+    def e2e_step():
+        vs_psi.parameters = pin_tree["psi"]            # H2D (pinned -> flat device buffer)
+        I_op.target.parameters = pin_tree["phi"]
+        vs_psi.reset()
+        I_op.target.reset()
+        st, grad = vs_psi.expect_and_grad(I_op)
+        grad_host.copy_(vs_psi._last_flat_grad, non_blocking=True)   # D2H
+        torch.cuda.synchronize()
+        return st
+
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        for k in ("psi", "phi"):
-            for d, p in zip(devp[k], pinned[k]):
-                if d is not None:
-                    d.copy_(p, non_blocking=True)
-        sums, L, grad = eng.step(specs["psi"], specs["phi"])
-        grad_host.copy_(grad, non_blocking=True)
-        sums_host.copy_(sums, non_blocking=True)
-        torch.cuda.synchronize()
+        st_e2e = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -235,6 +275,22 @@ def run_b200(args):
         mufu_per_eval = 2.25                                          # ex2 + cos + lg2/4
         peak = mufu / mufu_per_eval
         bytes_per_launch = eng.local_chains * w["chain_length"] * eng.W32 * 4 + N * M * 8
+        _, bf16_peak, _ = read_peaks()
+        S_loc = eng.S_local
+        # algorithmic GEMM FLOPs (one bf16-exact operand; the kernels execute 3x that as bf16 split terms)
+        fwd_flops = 4 * 2.0 * (N + 1) * 2 * M * S_loc
+        grad_flops = 2 * 2.0 * 2.0 * (N + 1) * 2 * (M + 1) * S_loc
+        other = [
+            {"kernel": "infid_fwd_tc_kernel (tcgen05)", "ms": fwd_ms, "bound": "tensor+sfu epilogue",
+             "achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+             "frac": fwd_flops / (fwd_ms * 1e-3) / 1e12 / bf16_peak,
+             "note": "algorithmic 4 forwards x 2(N+1)2M FLOP per pair; executed as 3 bf16 split UMMAs; the log-cosh "
+                     "epilogue (6 M complex log-cosh per pair), not the MMA, bounds this kernel"},
+            {"kernel": "infid_grad_tc_kernel (tcgen05)", "ms": grad_ms, "bound": "tensor+sfu epilogue",
+             "achieved": grad_flops / (grad_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+             "frac": grad_flops / (grad_ms * 1e-3) / 1e12 / bf16_peak,
+             "note": "algorithmic (forward + X^T Y) for sigma and eta tiles; executed as 3 bf16 split UMMAs each"},
+        ]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -246,7 +302,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "sfu", "kernel": "sample_plain_kernel", "achieved": achieved / 1e9,
                          "peak": peak / 1e9, "unit": "G logcosh-evals/s", "frac": achieved / peak,
-                         "traffic": None,
+                         "traffic": 642048,
                          "note": (f"the dominant kernel is MUFU-bound, neither HBM- nor tensor-bound: algorithmic work = "
                                   f"{evals_per_launch:.3e} Re-logcosh evals per launch (chains x sweeps x N x M) at "
                                   f"{mufu_per_eval} MUFU each; peak = MUFU.EX2 rate measured by nkfb_microbench in this "
@@ -255,7 +311,10 @@ def run_b200(args):
                                   f"{samp_ms / (ms_total / args.steps):.3f}"),
                          "hbm_view": {"bound": "hbm", "achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_gbs,
                                       "unit": "GB/s", "frac": bytes_per_launch / t_launch / 1e9 / hbm_gbs,
-                                      "peak_source": how}},
+                                      "peak_source": how},
+                         "traffic_note": "dram__bytes_read+write of one sampler launch from profiles/r01_ncu_top_kernels.md "
+                                         "(0.63 MB read + 12 KB written: parameters and packed samples stay in L2)",
+                         "other_kernels": other},
             "result": {"infidelity": infid, "acceptance": (eng.n_accepted.sum().item() /
                                                             (2.0 * eng.local_chains * sweeps * N * eng.steps_done))},
         }

@@ -271,7 +271,7 @@ static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs
   const char *forceL = getenv("NKFB_SAMP_L");  // tuning override
   for (int q = 0; q < 4; ++q) {
     const int L = Ls[q], K = (M + L - 1) / L;
-    if (K > 16) continue;
+    if (K > 16 && !(forceL && atoi(forceL) == L)) continue;
     if (forceL && atoi(forceL) == L) {
       bestL = L;
       break;

@@ -42,6 +42,9 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int K, co
       case 4: return launch_plain<NKFB_RT, 32, 13, 1, 4>(h, net, a, ws, st);
       case 5: return launch_plain<NKFB_RT, 32, 13, 1, 5>(h, net, a, ws, st);
       case 6: return launch_plain<NKFB_RT, 32, 13, 2, 3>(h, net, a, ws, st);
+      case 7: return launch_plain<NKFB_RT, 32, 13, 1, 4, true>(h, net, a, ws, st);
+      case 8: return launch_plain<NKFB_RT, 32, 13, 2, 4, true>(h, net, a, ws, st);
+      case 9: return launch_plain<NKFB_RT, 32, 13, 1, 6, true>(h, net, a, ws, st);
       default: break;
     }
   }
@@ -51,9 +54,20 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int K, co
     const char *v = getenv("NKFB_SAMP_VARIANT");
     const int iv = v ? atoi(v) : 0;
     switch (iv) {
-      case 11: return launch_plain<NKFB_RT, 16, 25, 1, 1>(h, net, a, ws, st);
-      case 12: return launch_plain<NKFB_RT, 16, 25, 1, 3>(h, net, a, ws, st);
-      case 13: return launch_plain<NKFB_RT, 16, 25, 1, 4>(h, net, a, ws, st);
+      case 11: return launch_plain<NKFB_RT, 16, 25, 1, 1, true>(h, net, a, ws, st);
+      case 12: return launch_plain<NKFB_RT, 16, 25, 1, 4, true>(h, net, a, ws, st);
+      case 13: return launch_plain<NKFB_RT, 16, 25, 1, 5, true>(h, net, a, ws, st);
+      default: break;
+    }
+  }
+#endif
+#if NKFB_L == 8 && defined(NKFB_TUNE)
+  if (K == 50 && sizeof(NKFB_RT) == 4) {
+    const char *v = getenv("NKFB_SAMP_VARIANT");
+    const int iv = v ? atoi(v) : 0;
+    switch (iv) {
+      case 21: return launch_plain<NKFB_RT, 8, 50, 1, 1, true>(h, net, a, ws, st);
+      case 22: return launch_plain<NKFB_RT, 8, 50, 1, 3, true>(h, net, a, ws, st);
       default: break;
     }
   }

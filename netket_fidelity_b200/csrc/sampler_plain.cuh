@@ -109,6 +109,12 @@ struct RowLoader {
   __device__ __forceinline__ RowLoader(const R *Wp, int M_, int l_) : W(reinterpret_cast<const V *>(Wp)), M(M_), l(l_) {
     last_ok = (l + L * (K - 1)) < M;
   }
+  __device__ __forceinline__ const V *ptr(int row) const { return W + (int64_t)row * M + l; }
+  template <int k>
+  __device__ __forceinline__ V ld(const V *p) const {
+    if (k < K - 1) return __ldg(p + L * k);
+    return last_ok ? __ldg(p + L * (K - 1)) : P2<R>::mk(R(0), R(0));
+  }
   __device__ __forceinline__ void load(int row, V (&w)[K]) const {
     const V *p = W + (int64_t)row * M + l;
 #pragma unroll
@@ -119,7 +125,62 @@ struct RowLoader {
   }
 };
 
-template <typename R, int L, int K, int C, int MB>
+// Same sum as lane_lc for the PROPOSAL theta + d W[site, :], with the row streamed from L1/L2 instead of
+// held in registers (used when K is large: the row is re-streamed for the accepted update).
+template <typename R, int L, int K, int k>
+struct StreamStep {
+  using P = P2<R>;
+  using V = typename P::V;
+  static __device__ __forceinline__ void run(const RowLoader<R, L, K> &rows, const V *rp, V d2, const V (&th)[K],
+                                             R &sumabs, R &lg, V &prod) {
+    if constexpr (k + 1 < K) {
+      const V p0 = P::fma(d2, rows.template ld<k>(rp), th[k]);
+      const V p1 = P::fma(d2, rows.template ld<k + 1>(rp), th[k + 1]);
+      const R a0 = abs_(p0.x), a1 = abs_(p1.x);
+      const V T = P::mk(P::ex2(-a0), P::ex2(-a1));
+      const V Cc = P::mk(P::cosr(p0.y), P::cosr(p1.y));
+      const V u = P::fma(P::mk(R(2), R(2)), Cc, T);
+      prod = P::mul(prod, P::fma(T, u, P::mk(R(1), R(1))));
+      sumabs += a0;
+      sumabs += a1;
+      if (((k + 2) & 3) == 0) {
+        lg += P::lg2(prod.x * prod.y);
+        prod = P::mk(R(1), R(1));
+      }
+      StreamStep<R, L, K, k + 2>::run(rows, rp, d2, th, sumabs, lg, prod);
+    } else if constexpr (k < K) {  // odd tail
+      const V p0 = P::fma(d2, rows.template ld<k>(rp), th[k]);
+      const R a0 = abs_(p0.x);
+      const R t = P::ex2(-a0), c = P::cosr(p0.y);
+      prod.x *= ::fma(t, ::fma(R(2), c, t), R(1));
+      sumabs += a0;
+    }
+  }
+};
+
+template <typename R, int L, int K>
+__device__ __forceinline__ R lane_lc_stream(const RowLoader<R, L, K> &rows, const typename P2<R>::V *rp,
+                                            typename P2<R>::V d2, const typename P2<R>::V (&th)[K]) {
+  using P = P2<R>;
+  R sumabs = R(0), lg = R(0);
+  typename P::V prod = P::mk(R(1), R(1));
+  StreamStep<R, L, K, 0>::run(rows, rp, d2, th, sumabs, lg, prod);
+  if ((K & 3) != 0) lg += P::lg2(prod.x * prod.y);
+  return sumabs + lg;
+}
+
+template <typename R, int L, int K, int k>
+struct StreamUpdate {
+  using V = typename P2<R>::V;
+  static __device__ __forceinline__ void run(const RowLoader<R, L, K> &rows, const V *rp, V de2, V (&th)[K]) {
+    if constexpr (k < K) {
+      th[k] = P2<R>::fma(de2, rows.template ld<k>(rp), th[k]);
+      StreamUpdate<R, L, K, k + 1>::run(rows, rp, de2, th);
+    }
+  }
+};
+
+template <typename R, int L, int K, int C, int MB, bool STREAM>
 __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_plain_kernel(NetDev<R> net, const R *ws, const R s0,
                                                                             const R s1, SampArgs a) {
   using P = P2<R>;
@@ -226,76 +287,120 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_plain_kernel(NetDe
     const uint32_t my_rs = sel4(rs, comp);
     const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
 
-    // ---- proposal site and the row W[site, :]
-    V w[K];
-    int site = 0;
-    R ar = R(0);
-    if (shared_sites) {
-      site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
-      rows.load(site, w);
-      ar = __ldg(ar2 + site);
-    }
-
-    // ---- phase 1: per-lane partial sums for every chain of the group
-    R part[C], dd[C], logu[C];
-    uint32_t word[C];
-    int sitec[C];
+    if constexpr (STREAM) {
+      // ---- phase 1: the row W[site, :] is streamed through registers (L1-resident), nothing is kept
+      R part[C], dd[C], logu[C], arc[C];
+      uint32_t word[C];
+      int sitec[C];
+      int site = 0;
+      if (shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int slot = g * C + c;
-      const int src = slot + NCH * bi;
-      logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
-      if (!shared_sites) {
-        site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
-        rows.load(site, w);
-        ar = __ldg(ar2 + site);
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const int src = slot + NCH * bi;
+        logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
+        if (!shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
+        sitec[c] = site;
+        arc[c] = __ldg(ar2 + site);
+        word[c] = sig[slot * W32 + (site >> 5)];
+        const R xold = ((word[c] >> (site & 31)) & 1u) ? s1 : s0;
+        const R d = ssum - R(2) * xold;
+        dd[c] = d;
+        part[c] = ::fma(d * arc[c], invL, lane_lc_stream<R, L, K>(rows, rows.ptr(site), P::mk(d, d), th[c]));
       }
-      sitec[c] = site;
-      word[c] = sig[slot * W32 + (site >> 5)];
-      const R xold = ((word[c] >> (site & 31)) & 1u) ? s1 : s0;
-      const R d = ssum - R(2) * xold;  // x_new - x_old
-      dd[c] = d;
-      const V d2 = P::mk(d, d);
-      V p[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) p[k] = P::fma(d2, w[k], th[c][k]);
-      // the visible-bias term d * ar is spread over the L lanes so that the butterfly sum carries it
-      part[c] = ::fma(d * ar, invL, lane_lc<R, K>(p));
-      if (!shared_sites) {
-        // per-chain sites: the row differs from chain to chain, so finish this chain now
-        const R lcn = group_sum<L>(part[c]);
-        const bool acc = (logu[c] < lcn - lc[c]) && (chain0 + slot < a.n_chains);
-        const R de = acc ? d : R(0);
-        const V de2 = P::mk(de, de);
-#pragma unroll
-        for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
-        lc[c] = acc ? lcn - d * ar : lc[c];
-        if (acc && l == 0) {
-          sig[slot * W32 + (site >> 5)] = word[c] ^ (1u << (site & 31));
-          ++n_acc;
-        }
-      }
-    }
-    if (shared_sites) {
-      // ---- phase 2: the C butterfly reductions are independent and pipeline through the shuffle unit
+      // ---- phase 2: butterfly sums (every lane group of the warp reduces its own chain in the same shuffles)
 #pragma unroll
       for (int m = L / 2; m > 0; m >>= 1)
 #pragma unroll
         for (int c = 0; c < C; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], m);
-      // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 / |psi(x)|^2
+      // ---- phase 3: accept / reject; the row is re-streamed only if some chain of the warp moved
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int slot = g * C + c;
         const R d = dd[c];
         const bool acc = (logu[c] < part[c] - lc[c]) && (chain0 + slot < a.n_chains);
-        const R de = acc ? d : R(0);
-        const V de2 = P::mk(de, de);
-#pragma unroll
-        for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
-        lc[c] = acc ? part[c] - d * ar : lc[c];
+        if (__any_sync(0xffffffffu, acc)) {
+          const R de = acc ? d : R(0);
+          StreamUpdate<R, L, K, 0>::run(rows, rows.ptr(sitec[c]), P::mk(de, de), th[c]);
+        }
+        lc[c] = acc ? part[c] - d * arc[c] : lc[c];
         if (acc && l == 0) {
           sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
           ++n_acc;
+        }
+      }
+    } else {
+      // ---- proposal site and the row W[site, :]
+      V w[K];
+      int site = 0;
+      R ar = R(0);
+      if (shared_sites) {
+        site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
+        rows.load(site, w);
+        ar = __ldg(ar2 + site);
+      }
+
+      // ---- phase 1: per-lane partial sums for every chain of the group
+      R part[C], dd[C], logu[C];
+      uint32_t word[C];
+      int sitec[C];
+  #pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const int src = slot + NCH * bi;
+        logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
+        if (!shared_sites) {
+          site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
+          rows.load(site, w);
+          ar = __ldg(ar2 + site);
+        }
+        sitec[c] = site;
+        word[c] = sig[slot * W32 + (site >> 5)];
+        const R xold = ((word[c] >> (site & 31)) & 1u) ? s1 : s0;
+        const R d = ssum - R(2) * xold;  // x_new - x_old
+        dd[c] = d;
+        const V d2 = P::mk(d, d);
+        V p[K];
+  #pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = P::fma(d2, w[k], th[c][k]);
+        // the visible-bias term d * ar is spread over the L lanes so that the butterfly sum carries it
+        part[c] = ::fma(d * ar, invL, lane_lc<R, K>(p));
+        if (!shared_sites) {
+          // per-chain sites: the row differs from chain to chain, so finish this chain now
+          const R lcn = group_sum<L>(part[c]);
+          const bool acc = (logu[c] < lcn - lc[c]) && (chain0 + slot < a.n_chains);
+          const R de = acc ? d : R(0);
+          const V de2 = P::mk(de, de);
+  #pragma unroll
+          for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
+          lc[c] = acc ? lcn - d * ar : lc[c];
+          if (acc && l == 0) {
+            sig[slot * W32 + (site >> 5)] = word[c] ^ (1u << (site & 31));
+            ++n_acc;
+          }
+        }
+      }
+      if (shared_sites) {
+        // ---- phase 2: the C butterfly reductions are independent and pipeline through the shuffle unit
+  #pragma unroll
+        for (int m = L / 2; m > 0; m >>= 1)
+  #pragma unroll
+          for (int c = 0; c < C; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], m);
+        // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 / |psi(x)|^2
+  #pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int slot = g * C + c;
+          const R d = dd[c];
+          const bool acc = (logu[c] < part[c] - lc[c]) && (chain0 + slot < a.n_chains);
+          const R de = acc ? d : R(0);
+          const V de2 = P::mk(de, de);
+  #pragma unroll
+          for (int k = 0; k < K; ++k) th[c][k] = P::fma(de2, w[k], th[c][k]);
+          lc[c] = acc ? part[c] - d * ar : lc[c];
+          if (acc && l == 0) {
+            sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
+            ++n_acc;
+          }
         }
       }
     }
@@ -325,7 +430,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_plain_kernel(NetDe
   }
 }
 
-template <typename R, int L, int K, int C, int MB = 1>
+template <typename R, int L, int K, int C, int MB = 1, bool STREAM = false>
 static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws, cudaStream_t st) {
   constexpr int NCH = (32 / L) * C;
   const int W32 = (net->n_visible + 31) >> 5;
@@ -333,11 +438,11 @@ static int launch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &
   const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
   const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
   if (smem > 48 * 1024) {
-    cudaError_t rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, K, C, MB>,
+    cudaError_t rc = cudaFuncSetAttribute(sample_plain_kernel<R, L, K, C, MB, STREAM>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   }
-  sample_plain_kernel<R, L, K, C, MB><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
+  sample_plain_kernel<R, L, K, C, MB, STREAM><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
       make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

@@ -116,19 +116,26 @@ class InfidelityStep:
     def _allreduce(self, t):
         par.allreduce_sum_(t, self.group)
 
-    def estimate(self, psi, phi, return_grad=True):
-        """Pass A (+ pass B).  Returns (sums[8] device tensor, L (S_local,), grad (P,) complex | None)."""
+    def estimate(self, psi, phi, return_grad=True, events=None):
+        """Pass A (+ pass B).  Returns (sums[8] device tensor, L (S_local,), grad (P,) complex | None).
+        `events`: optional 3 CUDA events recorded before pass A, after pass A, after pass B (bench.py)."""
         cfg = self.cfg
         sig = self.sigma.view(-1, self.W32)
         eta = self.eta.view(-1, self.W32)
         self.acc.zero_()
+        if events:
+            events[0].record()
         log_val, L, rho1, _ = self.h.infidelity_fwd(psi, phi, sig, eta, cfg.local_states, cfg.cv_coeff, self.op1,
                                                     self.op2, self.op4, sums=self.sums)
+        if events:
+            events[1].record()
         self._allreduce(self.sums)
         grad = None
         if return_grad:
             self.h.infidelity_grad(psi, sig, eta, cfg.local_states, cfg.cv_coeff, log_val, rho1, self.sums,
                                    op2=self.op2, grad_acc=self.grad_acc)
+            if events:
+                events[2].record()
             self._allreduce(self.grad_acc)
             grad = self.h.grad_finalize(self.grad_acc, self.sums, self.P, self.cdtype)
         self.last = dict(log_val=log_val, L=L, rho1=rho1)

@@ -21,6 +21,16 @@ def _allreduce(t):
     allreduce_sum_(t)
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key = dev.index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
 def infidelity_expect(vstate: MCState, op, return_grad: bool):
     if op.hilbert != vstate.hilbert:
         raise TypeError("Hilbert spaces should match")
@@ -43,6 +53,16 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
         op1, op2, op4 = op._U._spec(dev), op._U_dagger._spec(dev), None
     if vstate._spec().code != target._spec().code:
         raise TypeError("the variational state and the target must share a parameter precision")
+    if vstate._samples_packed is None and target._samples_packed is None and target is not vstate:
+        # both chain families need fresh samples (the driver's reset(), driver/infidelity_optimizer.py:142-143):
+        # run the two sampler launches on two streams so that the tail of one overlaps the other
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        vstate.sample()
+        with torch.cuda.stream(side):
+            target.sample()
+        main.wait_stream(side)
     sigma = vstate.samples_packed()
     eta = target.samples_packed()
     if sigma.shape != eta.shape:
