@@ -106,6 +106,17 @@ const char *nkfb_last_error(nkfb_handle_t h);
 /* number of kernels this handle has launched so far (bench.py: gpu_launches) */
 int64_t nkfb_launch_count(nkfb_handle_t h);
 
+/* Options.  NKFB_OPT_SAMPLER_ALGO selects the plain-target Metropolis kernel of nkfb_sample:
+ *   0 (default) automatic: the multiplicative kernel (z = exp(-2 theta) tracked by complex multiplications,
+ *               no transcendental per hidden unit) in single precision, the additive one (theta tracked by
+ *               additions, EX2 + COS per hidden unit) in double precision;
+ *   1           always additive;   2  multiplicative wherever its range windows cover the parameters.
+ * Both sample the same chain from the same random numbers (they accept the same proposals up to the rounding
+ * of the log-ratio); the additive kernel is always launched behind the multiplicative ones and takes over when
+ * max_j (|Re b_j| + max|s| sum_i |Re W_ij|) exceeds their range. */
+enum { NKFB_OPT_SAMPLER_ALGO = 1 };
+int nkfb_set_option(nkfb_handle_t h, int key, int64_t value);
+
 /* ---- configurations <-> packed bits ------------------------------------- */
 /* x: device (B, N) of dtype NKFB_F32/NKFB_F64 holding local-state values. */
 int nkfb_pack(nkfb_handle_t h, const void *x, int x_dtype, int64_t B, int N,

@@ -22,8 +22,11 @@ SYMBOLS = [
     "nkfb_version", "nkfb_create", "nkfb_destroy", "nkfb_last_error", "nkfb_launch_count",
     "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample", "nkfb_sample_workspace_bytes",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
-    "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update",
+    "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update", "nkfb_set_option",
 ]
+
+OPT_SAMPLER_ALGO = 1
+SAMPLER_AUTO, SAMPLER_ADDITIVE, SAMPLER_MULTIPLICATIVE = 0, 1, 2
 
 
 class NkfbError(RuntimeError):
@@ -88,6 +91,7 @@ def load_library():
         lib.nkfb_chain_stats.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp]
         lib.nkfb_renyi2.argtypes = [vp, P(RbmT), vp, i64, vp, P(dbl), vp, vp, vp, vp, vp]
         lib.nkfb_microbench.argtypes = [vp, i32, i32, P(dbl), vp]
+        lib.nkfb_set_option.argtypes = [vp, i32, i64]
         lib.nkfb_optimizer_update.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, i64, i32, vp]
         for name in SYMBOLS:
             getattr(lib, name)  # AttributeError if the ABI drifted
@@ -221,6 +225,14 @@ class Handle:
     def launches(self):
         return int(self.lib.nkfb_launch_count(self.h))
 
+    def set_option(self, key, value):
+        self._check(self.lib.nkfb_set_option(self.h, int(key), int(value)), "nkfb_set_option")
+
+    def set_sampler_algo(self, algo):
+        """0 auto, 1 additive (theta tracked by additions), 2 multiplicative (z = exp(-2 theta) tracked by
+        complex multiplications); see include/nkfb200.h."""
+        self.set_option(OPT_SAMPLER_ALGO, algo)
+
     # ---------------------------------------------------------------- pack / unpack
     def pack(self, x, local_states):
         x = x.contiguous()
@@ -285,7 +297,7 @@ class Handle:
         return out
 
     def sample_workspace(self, net: RbmSpec):
-        """Scratch for the sampler's pre-scaled parameter copy (one per concurrently sampled state)."""
+        """Scratch for the sampler's parameter tables (one per concurrently sampled state)."""
         nbytes = int(self.lib.nkfb_sample_workspace_bytes(net.N, net.M, net.code))
         return torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
 

@@ -317,6 +317,17 @@ extern "C" int nkfb_chain_stats(nkfb_handle_t h, const void *L, int dtype, int64
   return NKFB_OK;
 }
 
+extern "C" int nkfb_set_option(nkfb_handle_t h, int key, int64_t value) {
+  if (!h) return NKFB_ERR_INVALID;
+  switch (key) {
+    case NKFB_OPT_SAMPLER_ALGO:
+      if (value < 0 || value > 2) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler algorithm must be 0 (auto), 1 or 2");
+      h->opt_sampler_algo = (int)value;
+      return NKFB_OK;
+    default: NKFB_FAIL(h, NKFB_ERR_INVALID, "unknown option %d", key);
+  }
+}
+
 extern "C" int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops_per_second, void *stream) {
   if (!h || !ops_per_second || iters < 1) return NKFB_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;

@@ -18,6 +18,7 @@ struct nkfb_handle_s {
   size_t ws2_bytes;
   void *ws3;       // scratch: bf16 splits of the RBM kernel for the tensor-core gradient
   size_t ws3_bytes;
+  int opt_sampler_algo;  // NKFB_OPT_SAMPLER_ALGO
 };
 
 #define NKFB_CHECK_CUDA(h, call)                                                        \

@@ -16,7 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "sampler_plain.cuh"
+#include "sampler_ratio.cuh"
 
 namespace nkfb {
 
@@ -239,12 +239,86 @@ int dispatch_plain_f64_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, i
 int dispatch_plain_f64_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
 int dispatch_plain_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int K, const void *ws, cudaStream_t);
 
+int dispatch_ratio_f32_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f32_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f32_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f32_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f64_L4(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f64_L8(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f64_L16(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+int dispatch_ratio_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, int NP, int gl_one, const void *ws, cudaStream_t);
+
+// workspace = [ratio-sampler tables (sampler_ratio.cuh) | pre-scaled parameters of the additive sampler]
+static size_t plain_ws_offset_reals(int N, int M) { return (ratio_ws_reals_max(N, M) + 63) & ~(size_t)63; }
+static size_t sampler_ws_total_reals(int N, int M) { return plain_ws_offset_reals(N, M) + sampler_ws_reals(N, M); }
+
+// lane-group width of the multiplicative sampler: least padded work among the instantiated shapes (<= 8 pairs per
+// lane, <= 16 on 32 lanes in single precision); 0 if the shape is not covered
+static int ratio_pick_L(int M, bool f32) {
+  int bestL = 0, bestWork = 1 << 30;
+  const int Ls[4] = {32, 16, 8, 4};
+  for (int q = 0; q < 4; ++q) {
+    const int L = Ls[q], NP = ratio_pairs(M, L);
+    if (NP > (L == 32 && f32 ? 16 : 8)) continue;
+    if (2 * L * NP < bestWork) {
+      bestWork = 2 * L * NP;
+      bestL = L;
+    }
+  }
+  return bestL;
+}
+
+// Multiplicative sampler: launches the kernels whose range windows tile [0, x2]; returns the upper end x2 of
+// the covered range in *covered (the additive kernel then takes X > x2), or leaves it at -1 if the shape is
+// not covered at all.
+static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, void *ws, cudaStream_t st,
+                          float *covered) {
+  const int M = net->n_hidden, N = net->n_visible;
+  const bool f32 = net->dtype == NKFB_F32;
+  const int bestL = ratio_pick_L(M, f32);
+  if (bestL == 0) return NKFB_OK;  // not covered: the additive sampler does the whole range
+  const int L = bestL, NP = ratio_pairs(M, L);
+  const size_t a0_off = ratio_a0_off(N, M, L), b_off = ratio_bound_off(N, M, L);
+  const size_t rsz = f32 ? 4 : 8;
+  NKFB_CHECK_CUDA(h, cudaMemsetAsync((char *)ws + b_off * rsz, 0, rsz, st));
+  {
+    const int64_t tot = (int64_t)2 * N * NP * L + N + M;
+    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+    if (f32)
+      prep_ratio_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), (float *)ws, L, NP, (float)a.s0,
+                                                     (float)a.s1, a0_off, b_off);
+    else
+      prep_ratio_params<double><<<grid, 256, 0, st>>>(make_netdev<double>(net), (double *)ws, L, NP, a.s0, a.s1,
+                                                      a0_off, b_off);
+    NKFB_LAUNCHED(h);
+  }
+  a.xbound = reinterpret_cast<const float *>((const char *)ws + b_off * rsz);
+  const int GW = NP < 4 ? NP : 4;
+  const float x1 = ratio_xmax(GW), x2 = ratio_xmax(1);
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && GW == 1) break;
+    a.xlo = pass == 0 ? -1.0f : x1;
+    a.xhi = pass == 0 ? x1 : x2;
+    int rc;
+    switch (L) {
+      case 32: rc = f32 ? dispatch_ratio_f32_L32(h, net, a, NP, pass, ws, st) : dispatch_ratio_f64_L32(h, net, a, NP, pass, ws, st); break;
+      case 16: rc = f32 ? dispatch_ratio_f32_L16(h, net, a, NP, pass, ws, st) : dispatch_ratio_f64_L16(h, net, a, NP, pass, ws, st); break;
+      case 8: rc = f32 ? dispatch_ratio_f32_L8(h, net, a, NP, pass, ws, st) : dispatch_ratio_f64_L8(h, net, a, NP, pass, ws, st); break;
+      default: rc = f32 ? dispatch_ratio_f32_L4(h, net, a, NP, pass, ws, st) : dispatch_ratio_f64_L4(h, net, a, NP, pass, ws, st); break;
+    }
+    if (rc != NKFB_OK) return rc;
+  }
+  *covered = x2;
+  return NKFB_OK;
+}
+
 // lane-group width with the least padded work (ties -> wider group); K = ceil(M / L) <= 16 (32 for L = 32)
-static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, void *ws, size_t ws_bytes,
+static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a_in, void *ws, size_t ws_bytes,
                           cudaStream_t st) {
   const int M = net->n_hidden, N = net->n_visible;
-  // pre-scaled parameter copy (X = 2 log2e Re, Y = 2 Im) in the caller's scratch or the handle's
-  const size_t need = sampler_ws_reals(N, M) * (net->dtype == NKFB_F32 ? 4 : 8);
+  SampArgs a = a_in;
+  // sampler tables in the caller's scratch or the handle's
+  const size_t need = sampler_ws_total_reals(N, M) * (net->dtype == NKFB_F32 ? 4 : 8);
   if (ws) {
     if (ws_bytes < need) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler workspace too small: %zu < %zu bytes", ws_bytes, need);
   } else {
@@ -257,6 +331,24 @@ static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs
     }
     ws = h->ws;
   }
+  // algorithm: 0 auto (multiplicative in single precision, additive in double), 1 additive, 2 multiplicative.
+  // The multiplicative kernels cover X <= x2 (sampler_ratio.cuh); the additive kernel is always launched
+  // behind them for X > x2, and alone when the shape is not covered.
+  int algo = h->opt_sampler_algo;
+  if (const char *e = getenv("NKFB_SAMPLER_ALGO")) algo = atoi(e);
+  if (algo == 2 || (algo == 0 && net->dtype == NKFB_F32)) {
+    float covered = -1.0f;
+    const int rc = dispatch_ratio(h, net, a, ws, st, &covered);
+    if (rc != NKFB_OK) return rc;
+    if (covered >= 0.0f) {
+      const int L = ratio_pick_L(M, net->dtype == NKFB_F32);
+      a.xbound = reinterpret_cast<const float *>((const char *)ws +
+                                                 ratio_bound_off(N, M, L) * (net->dtype == NKFB_F32 ? 4 : 8));
+      a.xlo = covered;
+      a.xhi = __builtin_inff();
+    }
+  }
+  ws = (char *)ws + plain_ws_offset_reals(N, M) * (net->dtype == NKFB_F32 ? 4 : 8);
   {
     const int64_t tot = (int64_t)N * M + M + N;
     const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
@@ -362,5 +454,5 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
 
 extern "C" size_t nkfb_sample_workspace_bytes(int n_visible, int n_hidden, int dtype) {
   if (n_visible < 1 || n_hidden < 1) return 0;
-  return sampler_ws_reals(n_visible, n_hidden) * (dtype == NKFB_F32 ? 4 : 8);
+  return sampler_ws_total_reals(n_visible, n_hidden) * (dtype == NKFB_F32 ? 4 : 8);
 }

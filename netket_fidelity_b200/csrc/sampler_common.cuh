@@ -17,8 +17,18 @@ struct SampArgs {
   double s0, s1;
   uint32_t *chain_state, *samples;
   unsigned long long *n_accepted;
+  // range window of the plain-target kernels (sampler_ratio.cuh): a kernel runs iff xbound == nullptr or
+  // xlo < *xbound <= xhi, so that exactly one of the kernels launched back to back does the work
+  const float *xbound;
+  float xlo, xhi;
   OpDev op;
 };
+
+__device__ __forceinline__ bool samp_window_ok(const SampArgs &a) {
+  if (a.xbound == nullptr) return true;
+  const float X = *a.xbound;
+  return X > a.xlo && X <= a.xhi;
+}
 
 template <typename R>
 struct SMath;

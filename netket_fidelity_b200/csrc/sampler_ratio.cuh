@@ -1,0 +1,387 @@
+// Metropolis-local sampler for a plain RBM target |psi|^2, MULTIPLICATIVE form ("ratio sampler").
+//
+// Instead of the hidden pre-activations theta_j the chain keeps  z_j = exp(-2 theta_j)  (complex).
+// A single-spin flip at site i with x_new - x_old = d multiplies it by a constant of the parameters,
+//     z'_j = z_j * q_ij,   q_ij = exp(-2 d W_ij)          (two tables: d = +(s1 - s0) and d = -(s1 - s0)),
+// and because  cosh(theta) = e^theta (1 + z) / 2  the acceptance ratio needs no transcendental per unit:
+//     log2 |psi(x')|^2 - log2 |psi(x)|^2 = A_i(d) + sum_j [ log2 |1 + z'_j|^2 - log2 |1 + z_j|^2 ],
+//     A_i(d) = 2 log2(e) d (Re a_i + sum_j Re W_ij).
+// Per hidden unit and proposal: one complex multiply, |1 + z'|^2 and one factor of a running product --
+// on sm_100 eight packed-FP32 instructions (FMUL2 / FFMA2 / FADD2) per PAIR of units -- and one MUFU.LG2 per
+// GL pairs (the logs of 2 GL units are taken from their product).  The kernel is bound by the FP32 pipe and
+// by the L1 data path that streams the q rows (16 B per pair and chain), not by the MUFU pipe as the additive
+// sampler (sampler_plain.cuh: EX2 + COS per unit) is.
+//
+// Range: a product of 2 GL factors |1 + z|^2 <= (1 + e^{2X})^2 must stay below 2^126, X = max_j (|Re b_j| +
+// max|s| sum_i |Re W_ij|) >= |Re theta_j| for every configuration.  prep_ratio_params writes X next to the
+// tables; every sampler kernel starts by comparing X with its own window (SampArgs::xlo, xhi) and returns
+// immediately when it is not the one that covers X, so the host launches [ratio GL=4 | ratio GL=1 | additive]
+// back to back without reading anything back and exactly one of them does the work.
+//
+// Random numbers, site sequences, layouts and the emitted samples follow sampler_plain.cuh exactly (the two
+// kernels accept the same proposals up to rounding of the log-ratio).
+//
+// Template parameters: R real type; L lanes per chain group (4/8/16/32); NP PAIRS of hidden units per lane
+// (pair p of lane l = units 2 L p + l and 2 L p + L + l); C chains per lane group; GL pairs per logarithm;
+// MB minimum resident CTAs per SM.
+#pragma once
+
+#include "sampler_plain.cuh"
+
+namespace nkfb {
+
+template <typename R>
+struct V4T;
+template <>
+struct V4T<float> {
+  float2 lo, hi;
+  static __device__ __forceinline__ V4T<float> ld(const float *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    V4T<float> r;
+    r.lo = make_float2(v.x, v.y);
+    r.hi = make_float2(v.z, v.w);
+    return r;
+  }
+};
+template <>
+struct V4T<double> {
+  double2 lo, hi;
+  static __device__ __forceinline__ V4T<double> ld(const double *p) {
+    V4T<double> r;
+    r.lo = __ldg(reinterpret_cast<const double2 *>(p));
+    r.hi = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return r;
+  }
+};
+
+__device__ __forceinline__ float2 add2_(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ double2 add2_(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 neg2_(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ double2 neg2_(double2 a) { return make_double2(-a.x, -a.y); }
+
+// ---- workspace layout (reals of type R):  Q [2][N][NP * L][4]  |  A0 [N]  |  pad to 4  |  X (float, 1 word)
+inline int ratio_pairs(int M, int L) { return (M + 2 * L - 1) / (2 * L); }
+inline size_t ratio_q_reals(int N, int M, int L) { return (size_t)8 * N * ratio_pairs(M, L) * L; }
+inline size_t ratio_a0_off(int N, int M, int L) { return ratio_q_reals(N, M, L); }
+inline size_t ratio_bound_off(int N, int M, int L) { return (ratio_q_reals(N, M, L) + (size_t)N + 3) & ~(size_t)3; }
+// upper bound over every lane-group width (NP * L <= M / 2 + 32)
+inline size_t ratio_ws_reals_max(int N, int M) { return (size_t)8 * N * ((M + 1) / 2 + 32) + (size_t)N + 8; }
+
+// largest X for which a product of 2 GL factors (1 + e^{2X})^2 stays below 2^126 (2 % margin)
+inline float ratio_xmax(int GL) {
+  const double lim = 126.0 * LN2 / (4.0 * GL);  // ln(1 + e^{2X}) < lim
+  return (float)(0.98 * 0.5 * log(expm1(lim)));
+}
+
+template <typename R>
+__global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s1, size_t a0_off, size_t bound_off) {
+  const int N = net.N, M = net.M;
+  const int64_t slots_per_tab = (int64_t)N * NP * L;
+  const int64_t n_slots = 2 * slots_per_tab;
+  const double dx = (double)s1 - (double)s0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_slots + N + M;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    if (idx < n_slots) {
+      const int tab = idx >= slots_per_tab;
+      const int64_t rem = idx - tab * slots_per_tab;
+      const int i = (int)(rem / (NP * L));
+      const int pl = (int)(rem - (int64_t)i * NP * L);
+      const int p = pl / L, l = pl - p * L;
+      const R sgn = (R)(tab == 0 ? -2.0 * dx : 2.0 * dx);  // table 0: flip s0 -> s1 (d = +dx), q = exp(-2 d W)
+      R out[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = 2 * L * p + u * L + l;
+        R qr = R(1), qi = R(0);
+        if (j < M) {
+          const R wr = net.W[2 * ((int64_t)i * M + j)], wi = net.W[2 * ((int64_t)i * M + j) + 1];
+          const R e = exp_(sgn * wr);
+          R sn, cs;
+          sincos_(sgn * wi, &sn, &cs);
+          qr = e * cs;
+          qi = e * sn;
+        }
+        out[u] = qr;
+        out[2 + u] = qi;
+      }
+      st4(ws + 4 * idx, out);
+    } else if (idx < n_slots + N) {
+      const int i = (int)(idx - n_slots);
+      double acc = net.a ? (double)net.a[2 * i] : 0.0;
+      for (int j = 0; j < M; ++j) acc += (double)net.W[2 * ((int64_t)i * M + j)];
+      ws[a0_off + i] = (R)(2.0 * LOG2E * dx * acc);
+    } else {
+      const int j = (int)(idx - n_slots - N);
+      const double smax = fmax(fabs((double)s0), fabs((double)s1));
+      double acc = 0.0;
+      for (int i = 0; i < N; ++i) acc += fabs((double)net.W[2 * ((int64_t)i * M + j)]);
+      acc = acc * smax + (net.b ? fabs((double)net.b[2 * j]) : 0.0);
+      float xb = __double2float_ru(acc);
+      if (!(xb == xb)) xb = __int_as_float(0x7f800000);  // NaN parameters -> no fast path
+      atomicMax(reinterpret_cast<unsigned int *>(ws + bound_off), __float_as_uint(xb));  // xb >= 0: bit order = value order
+    }
+  }
+}
+
+template <typename R, int L, int NP, int C, int GL, int MB>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDev<R> net, const R *ws, const R s0,
+                                                                            const R s1, SampArgs a) {
+  using P = P2<R>;
+  using V = typename P::V;
+  using V4 = V4T<R>;
+  constexpr int G = 32 / L;      // chain groups per warp
+  constexpr int NCH = G * C;     // chains per warp
+  constexpr int BLK = 32 / NCH;  // Philox blocks per chain per RNG batch
+  constexpr int SB = 4 * BLK;    // MH steps per RNG batch
+  extern __shared__ uint32_t sig_all[];
+  if (!samp_window_ok(a)) return;
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / L, l = lane % L;
+  uint32_t *sig = sig_all + (size_t)warp * NCH * W32;  // [NCH][W32]
+  const int64_t warp_global = (int64_t)blockIdx.x * SAMP_WARPS + warp;
+  const int64_t chain0 = warp_global * NCH;  // first local chain of this warp
+  if (chain0 >= a.n_chains) return;
+  const int row_reals = 4 * NP * L;  // reals per (table, site) row
+  const R *Q = ws + 4 * l;
+  const R *A0 = ws + (size_t)8 * N * NP * L;
+  const V one = P::mk(R(1), R(1));
+
+  // ---- load / initialise configurations (identical to sample_plain_kernel)
+  for (int idx = lane; idx < NCH * W32; idx += 32) {
+    const int slot = idx / W32, w = idx - slot * W32;
+    const int64_t ch = chain0 + slot;
+    uint32_t v = 0;
+    if (ch < a.n_chains) {
+      if (a.init_random) {
+        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + ch), (uint32_t)TAG_INIT};
+        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+      } else {
+        v = a.chain_state[ch * W32 + w];
+      }
+      const int nb = N - 32 * w;
+      if (nb < 32) v &= (1u << nb) - 1u;
+    }
+    sig[idx] = v;
+  }
+  __syncwarp();
+
+  // ---- theta from scratch (pairs of units), then z = exp(-2 theta); padded units carry z = 0
+  V Zr[C][NP], Zi[C][NP];
+  {
+    const V *cW = reinterpret_cast<const V *>(net.W);
+    const V *cb = reinterpret_cast<const V *>(net.b);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int j0 = 2 * L * p + l, j1 = j0 + L;
+      const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(R(0), R(0));
+      const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(R(0), R(0));
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        Zr[c][p] = P::mk(b0.x, b1.x);
+        Zi[c][p] = P::mk(b0.y, b1.y);
+      }
+    }
+    for (int i = 0; i < N; ++i) {
+      V wr[NP], wi[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(R(0), R(0));
+        const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(R(0), R(0));
+        wr[p] = P::mk(w0.x, w1.x);
+        wi[p] = P::mk(w0.y, w1.y);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const R xv = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+        const V xx = P::mk(xv, xv);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          Zr[c][p] = P::fma(xx, wr[p], Zr[c][p]);
+          Zi[c][p] = P::fma(xx, wi[p], Zi[c][p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        R e0 = exp_(R(-2) * Zr[c][p].x), e1 = exp_(R(-2) * Zr[c][p].y);
+        R sn0, cs0, sn1, cs1;
+        sincos_(R(-2) * Zi[c][p].x, &sn0, &cs0);
+        sincos_(R(-2) * Zi[c][p].y, &sn1, &cs1);
+        if (j0 >= M) e0 = R(0);
+        if (j1 >= M) e1 = R(0);
+        Zr[c][p] = P::mk(e0 * cs0, e1 * cs1);
+        Zi[c][p] = P::mk(e0 * sn0, e1 * sn1);
+      }
+  }
+  // per-LANE cache of sum_j log2 |1 + z_j|^2 over the lane's units (never reduced: only differences are)
+  R lg[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    R acc = R(0);
+    V prod = one;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const V aa = add2_(Zr[c][p], one);
+      V m = P::mul(aa, aa);
+      m = P::fma(Zi[c][p], Zi[c][p], m);
+      prod = P::mul(prod, m);
+      if (((p + 1) % GL) == 0 || p == NP - 1) {
+        acc += P::lg2(prod.x * prod.y);
+        prod = one;
+      }
+    }
+    lg[c] = acc;
+  }
+
+  unsigned n_acc = 0;
+  const uint32_t n_steps = (uint32_t)(a.n_discard + a.chain_length) * (uint32_t)a.sweep_size;
+  const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));  // position of step 0 inside its batch
+  const uint64_t batch0 = a.step_offset - phase;
+  u32x4 rs = {0, 0, 0, 0};
+  R lu[4] = {R(0), R(0), R(0), R(0)};
+  int until_emit = a.sweep_size, sweep = 0;
+  const bool shared_sites = (a.site_mode == 0);
+
+  for (uint32_t s = 0; s < n_steps; ++s) {
+    const uint32_t pos = s + phase;        // steps since batch0
+    const int tb = (int)(pos & (SB - 1));  // position inside the RNG batch
+    if (tb == 0 || s == 0) {
+      // refill: lane r serves chain slot r % NCH with Philox block (batch start)/4 + r / NCH
+      const uint64_t bb = batch0 + (uint64_t)(pos - tb);
+      const uint64_t blk = (bb >> 2) + (uint64_t)(lane / NCH);
+      const uint32_t chid = (uint32_t)(a.chain_offset + chain0 + (lane % NCH));
+      u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
+      const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
+      lu[0] = SMath<R>::log2u(ru.x);
+      lu[1] = SMath<R>::log2u(ru.y);
+      lu[2] = SMath<R>::log2u(ru.z);
+      lu[3] = SMath<R>::log2u(ru.w);
+      if (shared_sites) {
+        const uint64_t sblk = (bb >> 2) + (uint64_t)(lane % BLK);
+        u32x4 c2 = {(uint32_t)sblk, (uint32_t)(sblk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
+        rs = philox4x32_10(c2, a.k0, a.k1);
+      } else {
+        ctr.w = (uint32_t)TAG_SITE_CHAIN;
+        rs = philox4x32_10(ctr, a.k0, a.k1);
+      }
+    }
+    const int bi = tb >> 2, comp = tb & 3;
+    const uint32_t my_rs = sel4(rs, comp);
+    const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
+
+    int site = 0;
+    if (shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
+
+    // ---- phase 1: proposals z' = z q and the per-lane change of sum_j log2 |1 + z_j|^2
+    V nZr[C][NP], nZi[C][NP];
+    R part[C], lgn[C], logu[C], dA[C];
+    uint32_t word[C];
+    int sitec[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int slot = g * C + c;
+      const int src = slot + NCH * bi;
+      logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
+      if (!shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
+      sitec[c] = site;
+      word[c] = sig[slot * W32 + (site >> 5)];
+      const uint32_t bit = (word[c] >> (site & 31)) & 1u;
+      const R *rp = Q + (size_t)((int)bit * N + site) * row_reals;
+      const R a0 = __ldg(A0 + site);
+      dA[c] = bit ? -a0 : a0;
+      R acc = R(0);
+      V prod = one;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const V4 q = V4::ld(rp + 4 * L * p);  // lo = (Re q_j0, Re q_j1), hi = (Im q_j0, Im q_j1)
+        const V t = P::mul(Zi[c][p], q.hi);
+        const V nr = P::fma(Zr[c][p], q.lo, neg2_(t));
+        const V u = P::mul(Zi[c][p], q.lo);
+        const V ni = P::fma(Zr[c][p], q.hi, u);
+        nZr[c][p] = nr;
+        nZi[c][p] = ni;
+        const V aa = add2_(nr, one);
+        V m = P::mul(aa, aa);
+        m = P::fma(ni, ni, m);
+        prod = P::mul(prod, m);
+        if (((p + 1) % GL) == 0 || p == NP - 1) {
+          acc += P::lg2(prod.x * prod.y);
+          prod = one;
+        }
+      }
+      lgn[c] = acc;
+      part[c] = acc - lg[c];
+    }
+    // ---- phase 2: butterfly sums over the lane group (the C reductions are independent and pipeline)
+#pragma unroll
+    for (int m = L / 2; m > 0; m >>= 1)
+#pragma unroll
+      for (int c = 0; c < C; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], m);
+    // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 - log2 |psi(x)|^2
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int slot = g * C + c;
+      const bool acc = (logu[c] < part[c] + dA[c]) && (chain0 + slot < a.n_chains);
+      if (acc) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          Zr[c][p] = nZr[c][p];
+          Zi[c][p] = nZi[c][p];
+        }
+        lg[c] = lgn[c];
+        if (l == 0) {
+          sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
+          ++n_acc;
+        }
+      }
+    }
+    __syncwarp();
+
+    if (--until_emit == 0) {
+      until_emit = a.sweep_size;
+      if (sweep >= a.n_discard) {
+        const int ts = sweep - a.n_discard;
+        for (int idx = lane; idx < NCH * W32; idx += 32) {
+          const int slot = idx / W32, w32 = idx - slot * W32;
+          const int64_t ch = chain0 + slot;
+          if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w32] = sig[idx];
+        }
+      }
+      ++sweep;
+    }
+  }
+  for (int idx = lane; idx < NCH * W32; idx += 32) {
+    const int slot = idx / W32, w32 = idx - slot * W32;
+    const int64_t ch = chain0 + slot;
+    if (ch < a.n_chains) a.chain_state[ch * W32 + w32] = sig[idx];
+  }
+  if (a.n_accepted) {
+    n_acc = warp_sum(n_acc);
+    if (lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+  }
+}
+
+template <typename R, int L, int NP, int C, int GL, int MB>
+static int launch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws, cudaStream_t st) {
+  constexpr int NCH = (32 / L) * C;
+  const int W32 = (net->n_visible + 31) >> 5;
+  const int64_t warps = (a.n_chains + NCH - 1) / NCH;
+  const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
+  const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    cudaError_t rc = cudaFuncSetAttribute(sample_ratio_kernel<R, L, NP, C, GL, MB>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
+  }
+  sample_ratio_kernel<R, L, NP, C, GL, MB><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
+      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+}  // namespace nkfb

@@ -1,0 +1,89 @@
+// Instantiations of the multiplicative ("ratio") plain-target sampler for one (real type, lane-group width)
+// pair.  Compiled once per pair by the Makefile:  -DNKFB_RT=float|double -DNKFB_RN=f32|f64 -DNKFB_L=4|8|16|32
+#include <cstdlib>
+
+#include "sampler_ratio.cuh"
+
+namespace nkfb {
+
+#define NKFB_CAT_(a, b, c) a##b##_L##c
+#define NKFB_CAT(a, b, c) NKFB_CAT_(a, b, c)
+#define NKFB_FN NKFB_CAT(dispatch_ratio_, NKFB_RN, NKFB_L)
+
+// chains per lane group and minimum resident CTAs per SM: the state is 4 NP C registers (z) plus as many for
+// the proposal z', in units of sizeof(R) / 4
+template <typename R, int NP>
+struct RatioShape {
+  static constexpr bool f32 = sizeof(R) == 4;
+  static constexpr int C = f32 ? (NP <= 2 ? 4 : (NP <= 7 ? 2 : 1)) : (NP <= 2 ? 2 : 1);
+  static constexpr int MB = f32 ? (NP <= 4 ? 4 : (NP <= 7 ? 3 : (NP <= 8 ? 4 : (NP <= 12 ? 3 : 2)))) : (NP <= 4 ? 3 : 2);
+};
+
+template <int NP>
+static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_one, const void *ws, cudaStream_t st) {
+  using S = RatioShape<NKFB_RT, NP>;
+  constexpr int GW = NP < 4 ? NP : 4;
+  if (gl_one) return launch_ratio<NKFB_RT, NKFB_L, NP, S::C, 1, S::MB>(h, net, a, ws, st);
+  return launch_ratio<NKFB_RT, NKFB_L, NP, S::C, GW, S::MB>(h, net, a, ws, st);
+}
+
+// NP = 9..16 (M up to 1024 on 32 lanes): single precision only
+template <typename R>
+static int go_big(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, int gl_one, const void *ws,
+                  cudaStream_t st) {
+  if constexpr (sizeof(R) == 4) {
+    switch (NP) {
+      case 9: return go<9>(h, net, a, gl_one, ws, st);
+      case 10: return go<10>(h, net, a, gl_one, ws, st);
+      case 11: return go<11>(h, net, a, gl_one, ws, st);
+      case 12: return go<12>(h, net, a, gl_one, ws, st);
+      case 13: return go<13>(h, net, a, gl_one, ws, st);
+      case 14: return go<14>(h, net, a, gl_one, ws, st);
+      case 15: return go<15>(h, net, a, gl_one, ws, st);
+      default: return go<16>(h, net, a, gl_one, ws, st);
+    }
+  }
+  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "ratio sampler: %d unit pairs per lane needs single precision", NP);
+}
+
+// gl_one = 0: one logarithm per min(NP, 4) pairs;  gl_one = 1: one logarithm per pair (wider range of X)
+int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, int gl_one, const void *ws,
+            cudaStream_t st) {
+#if NKFB_L == 32 && defined(NKFB_TUNE)
+  // tuning variants of the north-star shape (M = 400 -> NP = 7), selected by NKFB_RATIO_VARIANT
+  if (NP == 7 && sizeof(NKFB_RT) == 4 && !gl_one) {
+    const char *v = getenv("NKFB_RATIO_VARIANT");
+    const int iv = v ? atoi(v) : 0;
+    switch (iv) {
+      case 1: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 3>(h, net, a, ws, st);
+      case 2: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 4>(h, net, a, ws, st);
+      case 3: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 4>(h, net, a, ws, st);
+      case 4: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 5>(h, net, a, ws, st);
+      case 5: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 6>(h, net, a, ws, st);
+      case 6: return launch_ratio<NKFB_RT, 32, 7, 2, 7, 3>(h, net, a, ws, st);
+      case 7: return launch_ratio<NKFB_RT, 32, 7, 2, 2, 3>(h, net, a, ws, st);
+      case 8: return launch_ratio<NKFB_RT, 32, 7, 3, 4, 2>(h, net, a, ws, st);
+      case 9: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 2>(h, net, a, ws, st);
+      default: break;
+    }
+  }
+#endif
+  switch (NP) {
+    case 1: return go<1>(h, net, a, gl_one, ws, st);
+    case 2: return go<2>(h, net, a, gl_one, ws, st);
+    case 3: return go<3>(h, net, a, gl_one, ws, st);
+    case 4: return go<4>(h, net, a, gl_one, ws, st);
+    case 5: return go<5>(h, net, a, gl_one, ws, st);
+    case 6: return go<6>(h, net, a, gl_one, ws, st);
+    case 7: return go<7>(h, net, a, gl_one, ws, st);
+    case 8: return go<8>(h, net, a, gl_one, ws, st);
+#if NKFB_L == 32
+    case 9: case 10: case 11: case 12: case 13: case 14: case 15: case 16:
+      return go_big<NKFB_RT>(h, net, a, NP, gl_one, ws, st);
+#endif
+    default: break;
+  }
+  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "ratio sampler: %d unit pairs per lane is not instantiated", NP);
+}
+
+}  // namespace nkfb

@@ -83,6 +83,75 @@ def test_fp64_composite_trajectories(h, U, M):
     assert nacc == nacc_ref
 
 
+@pytest.fixture
+def algo(h):
+    """Selects the plain-target kernel for one test and restores the automatic choice afterwards."""
+    def set_(a):
+        h.set_sampler_algo(a)
+    yield set_
+    h.set_sampler_algo(0)
+
+
+@pytest.mark.parametrize("N,M", LAYOUTS)
+@pytest.mark.parametrize("site_mode", [0, 1])
+def test_fp64_multiplicative_sampler_follows_the_same_trajectories(h, algo, N, M, site_mode):
+    """The multiplicative kernel (z = exp(-2 theta), sampler_ratio.cuh) consumes the same random numbers and
+    accepts the same proposals as the additive one; in float64 the two log-ratios differ by ~1e-13, so the
+    trajectories coincide with the float64 restatement of the additive algorithm."""
+    algo(2)
+    p = _net(N, M, 100 + N, 0.15)
+    n_chains, cl, nd = 7, 3, 2
+    ref, fin, nacc_ref = metropolis_local_b200(p, n_chains, cl, nd, N, seed=0x1234567890AB, site_mode=site_mode,
+                                               chain_offset=5, step_offset=3)
+    got, state, nacc = _run(h, p, torch.complex128, n_chains, cl, nd, N, 0x1234567890AB, site_mode,
+                            chain_offset=5, step_offset=3)
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(state.cpu().numpy().view(np.uint32), fin)
+    assert nacc == nacc_ref
+
+
+@pytest.mark.parametrize("std", [0.05, 0.3, 0.7, 2.5])
+def test_fp64_multiplicative_sampler_range_windows(h, algo, std):
+    """X = max_j (|Re b_j| + sum_i |Re W_ij|) grows with std through the three windows of the plain-target
+    kernels (one log per 4 pairs: X <= 2.67; one per pair: X <= 10.7; additive beyond): whichever kernel
+    takes the call, the trajectories are those of the restatement."""
+    algo(2)
+    N, M = 10, 20
+    p = _net(N, M, 77, std)
+    X = np.max(np.abs(p.bias.real) + np.abs(p.kernel.real).sum(0))
+    assert {0.05: X < 2.0, 0.3: 2.8 < X < 10.0, 0.7: 2.8 < X < 10.0, 2.5: X > 11.5}[std], X
+    ref, fin, nacc_ref = metropolis_local_b200(p, 9, 4, 2, N, seed=4711)
+    got, state, nacc = _run(h, p, torch.complex128, 9, 4, 2, N, 4711)
+    np.testing.assert_array_equal(got, ref)
+    assert nacc == nacc_ref
+
+
+def test_multiplicative_chains_continue_across_calls_and_shards(h, algo):
+    algo(2)
+    N, M = 10, 20
+    p = _net(N, M, 9, 0.2)
+    full, _, _ = _run(h, p, torch.complex128, 8, 6, 0, N, 77)
+    a, st, _ = _run(h, p, torch.complex128, 8, 3, 0, N, 77)
+    b, _, _ = _run(h, p, torch.complex128, 8, 3, 0, N, 77, step_offset=3 * N, state=st)
+    np.testing.assert_array_equal(np.concatenate([a, b], axis=1), full)
+    shard, _, _ = _run(h, p, torch.complex128, 4, 6, 0, N, 77, chain_offset=4)
+    np.testing.assert_array_equal(shard, full[4:])
+
+
+def test_fp32_samplers_agree_on_most_trajectories(h, algo):
+    """Single precision: the additive and the multiplicative kernel share random numbers and differ only in the
+    rounding of the log-ratio (~1e-5), so all but a few chains emit identical samples."""
+    N, M = 16, 64
+    p = _net(N, M, 3, 0.1)
+    algo(1)
+    a, _, na = _run(h, p, torch.complex64, 256, 8, 2, N, 5)
+    algo(2)
+    b, _, nb = _run(h, p, torch.complex64, 256, 8, 2, N, 5)
+    same = np.all(a.reshape(256, -1) == b.reshape(256, -1), axis=1).mean()
+    assert same > 0.9, same
+    assert abs(na - nb) < 0.01 * na
+
+
 def _z_scores(counts, p, inflate):
     S = counts.sum()
     return (counts / S - p) / np.sqrt(p * (1 - p) * inflate / S)
@@ -91,7 +160,9 @@ def _z_scores(counts, p, inflate):
 @pytest.mark.parametrize("N,M", [(4, 4), (6, 12), (8, 40), (10, 80), (12, 300)])
 @pytest.mark.parametrize("cd", [torch.complex64, torch.complex128])
 @pytest.mark.parametrize("site_mode", [0, 1])
-def test_sampler_matches_exact_distribution(h, N, M, cd, site_mode):
+@pytest.mark.parametrize("sampler", [1, 2])
+def test_sampler_matches_exact_distribution(h, algo, N, M, cd, site_mode, sampler):
+    algo(sampler)
     p = _net(N, M, 7 * N, 0.5 / np.sqrt(M))
     n_chains, cl = 4096, 64
     got, _, nacc = _run(h, p, cd, n_chains, cl, 30, N, 2024 + site_mode, site_mode)
@@ -103,6 +174,28 @@ def test_sampler_matches_exact_distribution(h, N, M, cd, site_mode):
     assert np.max(np.abs(z[keep])) < 5.0, np.max(np.abs(z[keep]))
     acc_rate = nacc / (n_chains * (cl + 30) * N)
     assert 0.05 < acc_rate <= 1.0
+
+
+@pytest.mark.parametrize("B", [0.0, 4.0, 14.0])
+@pytest.mark.parametrize("sampler", [1, 2])
+def test_fp32_samplers_saturated_hidden_units(h, algo, B, sampler):
+    """Single precision with hidden biases +-B: X = max_j (|Re b_j| + sum_i |Re W_ij|) = 1.6 / 5.6 / 15.6 falls
+    in the first (one log per 4 pairs), second (one log per pair) and third (additive kernel) range window of
+    the multiplicative sampler; z = exp(-2 theta) spans e^{+-2X}.  The distribution itself stays broad (large
+    biases saturate cosh), so the chains mix within a sweep and the z-scores are meaningful."""
+    algo(sampler)
+    N, M = 10, 24
+    p = _net(N, M, 21, 0.15)
+    p = RBMParams(p.kernel, p.bias + B * np.where(np.arange(M) % 2 == 0, 1.0, -1.0), p.visible_bias)
+    X = np.max(np.abs(p.bias.real) + np.abs(p.kernel.real).sum(0))
+    assert {0.0: X < 2.6, 4.0: 2.8 < X < 10.6, 14.0: X > 10.8}[B], X
+    got, _, _ = _run(h, p, torch.complex64, 4096, 64, 30, N, 99)
+    x = unpack_np(got.reshape(-1, got.shape[-1]), N)
+    counts = np.bincount(states_to_numbers(x), minlength=2 ** N)
+    pe = exact_distribution(make_logfun(p), N)
+    keep = pe * counts.sum() > 50
+    z = _z_scores(counts, pe, inflate=6.0)
+    assert np.max(np.abs(z[keep])) < 5.0, np.max(np.abs(z[keep]))
 
 
 @pytest.mark.parametrize("U", [oops.Rx(6, 2, 0.9), oops.Ry(6, 0, 0.7), oops.Hadamard(6, 5),
