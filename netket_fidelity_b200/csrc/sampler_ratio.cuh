@@ -123,7 +123,29 @@ __global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s
   }
 }
 
-template <typename R, int L, int NP, int C, int GL, int MB>
+// sum over a lane group of L lanes.  Full warps use one integer REDUX on a 2^-20 fixed-point image of the
+// addends (|v| <= 60 on every lane, else the butterfly): the reduction sits on the critical path of every
+// Metropolis step and a butterfly costs five dependent shuffle + add rounds.
+template <int L>
+__device__ __forceinline__ float group_sum_fast(float v) {
+  if constexpr (L == 32) {
+    if (__all_sync(0xffffffffu, fabsf(v) <= 60.0f)) {
+      const int s = __reduce_add_sync(0xffffffffu, __float2int_rn(v * 1048576.0f));
+      return (float)s * (1.0f / 1048576.0f);
+    }
+  }
+  return group_sum<L>(v);
+}
+template <int L>
+__device__ __forceinline__ double group_sum_fast(double v) { return group_sum<L>(v); }
+
+// MODE 0: the proposal z' is kept next to z and copied over it when the move is accepted.
+// MODE 1: z is multiplied in place and multiplied back by the inverse row (the other table, same site) when the
+//         move is REJECTED: half the registers, no copies; z is recomputed from the configuration every
+//         RATIO_REFRESH sweeps, which bounds the rounding drift of the products (both modes).
+constexpr int RATIO_REFRESH = 32;
+
+template <typename R, int L, int NP, int C, int GL, int MB, int MODE>
 __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDev<R> net, const R *ws, const R s0,
                                                                             const R s1, SampArgs a) {
   using P = P2<R>;
@@ -166,78 +188,8 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDe
   }
   __syncwarp();
 
-  // ---- theta from scratch (pairs of units), then z = exp(-2 theta); padded units carry z = 0
   V Zr[C][NP], Zi[C][NP];
-  {
-    const V *cW = reinterpret_cast<const V *>(net.W);
-    const V *cb = reinterpret_cast<const V *>(net.b);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      const int j0 = 2 * L * p + l, j1 = j0 + L;
-      const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(R(0), R(0));
-      const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(R(0), R(0));
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        Zr[c][p] = P::mk(b0.x, b1.x);
-        Zi[c][p] = P::mk(b0.y, b1.y);
-      }
-    }
-    for (int i = 0; i < N; ++i) {
-      V wr[NP], wi[NP];
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        const int j0 = 2 * L * p + l, j1 = j0 + L;
-        const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(R(0), R(0));
-        const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(R(0), R(0));
-        wr[p] = P::mk(w0.x, w1.x);
-        wi[p] = P::mk(w0.y, w1.y);
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const R xv = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
-        const V xx = P::mk(xv, xv);
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          Zr[c][p] = P::fma(xx, wr[p], Zr[c][p]);
-          Zi[c][p] = P::fma(xx, wi[p], Zi[c][p]);
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        const int j0 = 2 * L * p + l, j1 = j0 + L;
-        R e0 = exp_(R(-2) * Zr[c][p].x), e1 = exp_(R(-2) * Zr[c][p].y);
-        R sn0, cs0, sn1, cs1;
-        sincos_(R(-2) * Zi[c][p].x, &sn0, &cs0);
-        sincos_(R(-2) * Zi[c][p].y, &sn1, &cs1);
-        if (j0 >= M) e0 = R(0);
-        if (j1 >= M) e1 = R(0);
-        Zr[c][p] = P::mk(e0 * cs0, e1 * cs1);
-        Zi[c][p] = P::mk(e0 * sn0, e1 * sn1);
-      }
-  }
-  // per-LANE cache of sum_j log2 |1 + z_j|^2 over the lane's units (never reduced: only differences are)
-  R lg[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    R acc = R(0);
-    V prod = one;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      const V aa = add2_(Zr[c][p], one);
-      V m = P::mul(aa, aa);
-      m = P::fma(Zi[c][p], Zi[c][p], m);
-      prod = P::mul(prod, m);
-      if (((p + 1) % GL) == 0 || p == NP - 1) {
-        acc += P::lg2(prod.x * prod.y);
-        prod = one;
-      }
-    }
-    lg[c] = acc;
-  }
-
+  R lg[C];  // per-LANE cache of sum_j log2 |1 + z_j|^2 over the lane's units (only differences are reduced)
   unsigned n_acc = 0;
   const uint32_t n_steps = (uint32_t)(a.n_discard + a.chain_length) * (uint32_t)a.sweep_size;
   const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));  // position of step 0 inside its batch
@@ -246,113 +198,203 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDe
   R lu[4] = {R(0), R(0), R(0), R(0)};
   int until_emit = a.sweep_size, sweep = 0;
   const bool shared_sites = (a.site_mode == 0);
+  const uint32_t seg_steps = (uint32_t)RATIO_REFRESH * (uint32_t)a.sweep_size;
 
-  for (uint32_t s = 0; s < n_steps; ++s) {
-    const uint32_t pos = s + phase;        // steps since batch0
-    const int tb = (int)(pos & (SB - 1));  // position inside the RNG batch
-    if (tb == 0 || s == 0) {
-      // refill: lane r serves chain slot r % NCH with Philox block (batch start)/4 + r / NCH
-      const uint64_t bb = batch0 + (uint64_t)(pos - tb);
-      const uint64_t blk = (bb >> 2) + (uint64_t)(lane / NCH);
-      const uint32_t chid = (uint32_t)(a.chain_offset + chain0 + (lane % NCH));
-      u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
-      const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
-      lu[0] = SMath<R>::log2u(ru.x);
-      lu[1] = SMath<R>::log2u(ru.y);
-      lu[2] = SMath<R>::log2u(ru.z);
-      lu[3] = SMath<R>::log2u(ru.w);
-      if (shared_sites) {
-        const uint64_t sblk = (bb >> 2) + (uint64_t)(lane % BLK);
-        u32x4 c2 = {(uint32_t)sblk, (uint32_t)(sblk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
-        rs = philox4x32_10(c2, a.k0, a.k1);
-      } else {
-        ctr.w = (uint32_t)TAG_SITE_CHAIN;
-        rs = philox4x32_10(ctr, a.k0, a.k1);
-      }
-    }
-    const int bi = tb >> 2, comp = tb & 3;
-    const uint32_t my_rs = sel4(rs, comp);
-    const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
-
-    int site = 0;
-    if (shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
-
-    // ---- phase 1: proposals z' = z q and the per-lane change of sum_j log2 |1 + z_j|^2
-    V nZr[C][NP], nZi[C][NP];
-    R part[C], lgn[C], logu[C], dA[C];
-    uint32_t word[C];
-    int sitec[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int slot = g * C + c;
-      const int src = slot + NCH * bi;
-      logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
-      if (!shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
-      sitec[c] = site;
-      word[c] = sig[slot * W32 + (site >> 5)];
-      const uint32_t bit = (word[c] >> (site & 31)) & 1u;
-      const R *rp = Q + (size_t)((int)bit * N + site) * row_reals;
-      const R a0 = __ldg(A0 + site);
-      dA[c] = bit ? -a0 : a0;
-      R acc = R(0);
-      V prod = one;
+  uint32_t s = 0;
+  while (s < n_steps) {
+    // ---- theta from scratch (pairs of units), then z = exp(-2 theta); padded units carry z = 0
+    {
+      const V *cW = reinterpret_cast<const V *>(net.W);
+      const V *cb = reinterpret_cast<const V *>(net.b);
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        const V4 q = V4::ld(rp + 4 * L * p);  // lo = (Re q_j0, Re q_j1), hi = (Im q_j0, Im q_j1)
-        const V t = P::mul(Zi[c][p], q.hi);
-        const V nr = P::fma(Zr[c][p], q.lo, neg2_(t));
-        const V u = P::mul(Zi[c][p], q.lo);
-        const V ni = P::fma(Zr[c][p], q.hi, u);
-        nZr[c][p] = nr;
-        nZi[c][p] = ni;
-        const V aa = add2_(nr, one);
-        V m = P::mul(aa, aa);
-        m = P::fma(ni, ni, m);
-        prod = P::mul(prod, m);
-        if (((p + 1) % GL) == 0 || p == NP - 1) {
-          acc += P::lg2(prod.x * prod.y);
-          prod = one;
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(R(0), R(0));
+        const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(R(0), R(0));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          Zr[c][p] = P::mk(b0.x, b1.x);
+          Zi[c][p] = P::mk(b0.y, b1.y);
         }
       }
-      lgn[c] = acc;
-      part[c] = acc - lg[c];
-    }
-    // ---- phase 2: butterfly sums over the lane group (the C reductions are independent and pipeline)
-#pragma unroll
-    for (int m = L / 2; m > 0; m >>= 1)
-#pragma unroll
-      for (int c = 0; c < C; ++c) part[c] += __shfl_xor_sync(0xffffffffu, part[c], m);
-    // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 - log2 |psi(x)|^2
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int slot = g * C + c;
-      const bool acc = (logu[c] < part[c] + dA[c]) && (chain0 + slot < a.n_chains);
-      if (acc) {
+      for (int i = 0; i < N; ++i) {
+        V wr[NP], wi[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          Zr[c][p] = nZr[c][p];
-          Zi[c][p] = nZi[c][p];
+          const int j0 = 2 * L * p + l, j1 = j0 + L;
+          const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(R(0), R(0));
+          const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(R(0), R(0));
+          wr[p] = P::mk(w0.x, w1.x);
+          wi[p] = P::mk(w0.y, w1.y);
         }
-        lg[c] = lgn[c];
-        if (l == 0) {
-          sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
-          ++n_acc;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const R xv = ((sig[(g * C + c) * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+          const V xx = P::mk(xv, xv);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            Zr[c][p] = P::fma(xx, wr[p], Zr[c][p]);
+            Zi[c][p] = P::fma(xx, wi[p], Zi[c][p]);
+          }
         }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int j0 = 2 * L * p + l, j1 = j0 + L;
+          R e0 = exp_(R(-2) * Zr[c][p].x), e1 = exp_(R(-2) * Zr[c][p].y);
+          R sn0, cs0, sn1, cs1;
+          sincos_(R(-2) * Zi[c][p].x, &sn0, &cs0);
+          sincos_(R(-2) * Zi[c][p].y, &sn1, &cs1);
+          if (j0 >= M) e0 = R(0);
+          if (j1 >= M) e1 = R(0);
+          Zr[c][p] = P::mk(e0 * cs0, e1 * cs1);
+          Zi[c][p] = P::mk(e0 * sn0, e1 * sn1);
+        }
+        R acc = R(0);
+        V prod = one;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const V aa = add2_(Zr[c][p], one);
+          V m = P::mul(aa, aa);
+          m = P::fma(Zi[c][p], Zi[c][p], m);
+          prod = P::mul(prod, m);
+          if (((p + 1) % GL) == 0 || p == NP - 1) {
+            acc += P::lg2(prod.x * prod.y);
+            prod = one;
+          }
+        }
+        lg[c] = acc;
       }
     }
-    __syncwarp();
 
-    if (--until_emit == 0) {
-      until_emit = a.sweep_size;
-      if (sweep >= a.n_discard) {
-        const int ts = sweep - a.n_discard;
-        for (int idx = lane; idx < NCH * W32; idx += 32) {
-          const int slot = idx / W32, w32 = idx - slot * W32;
-          const int64_t ch = chain0 + slot;
-          if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w32] = sig[idx];
+    const uint32_t s_end = (n_steps - s > seg_steps) ? s + seg_steps : n_steps;
+    for (; s < s_end; ++s) {
+      const uint32_t pos = s + phase;        // steps since batch0
+      const int tb = (int)(pos & (SB - 1));  // position inside the RNG batch
+      if (tb == 0 || s == 0) {
+        // refill: lane r serves chain slot r % NCH with Philox block (batch start)/4 + r / NCH
+        const uint64_t bb = batch0 + (uint64_t)(pos - tb);
+        const uint64_t blk = (bb >> 2) + (uint64_t)(lane / NCH);
+        const uint32_t chid = (uint32_t)(a.chain_offset + chain0 + (lane % NCH));
+        u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
+        const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
+        lu[0] = SMath<R>::log2u(ru.x);
+        lu[1] = SMath<R>::log2u(ru.y);
+        lu[2] = SMath<R>::log2u(ru.z);
+        lu[3] = SMath<R>::log2u(ru.w);
+        if (shared_sites) {
+          const uint64_t sblk = (bb >> 2) + (uint64_t)(lane % BLK);
+          u32x4 c2 = {(uint32_t)sblk, (uint32_t)(sblk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
+          rs = philox4x32_10(c2, a.k0, a.k1);
+        } else {
+          ctr.w = (uint32_t)TAG_SITE_CHAIN;
+          rs = philox4x32_10(ctr, a.k0, a.k1);
         }
       }
-      ++sweep;
+      const int bi = tb >> 2, comp = tb & 3;
+      const uint32_t my_rs = sel4(rs, comp);
+      const R my_lu = comp == 0 ? lu[0] : (comp == 1 ? lu[1] : (comp == 2 ? lu[2] : lu[3]));
+
+      int site = 0;
+      if (shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, bi), (uint32_t)N);
+
+      // ---- phase 1: proposals z' = z q and the per-lane change of sum_j log2 |1 + z_j|^2
+      V nZr[MODE == 0 ? C : 1][MODE == 0 ? NP : 1], nZi[MODE == 0 ? C : 1][MODE == 0 ? NP : 1];
+      R part[C], lgn[C], logu[C], dA[C];
+      uint32_t word[C];
+      int sitec[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const int src = slot + NCH * bi;
+        logu[c] = __shfl_sync(0xffffffffu, my_lu, src);
+        if (!shared_sites) site = (int)__umulhi(__shfl_sync(0xffffffffu, my_rs, src), (uint32_t)N);
+        sitec[c] = site;
+        word[c] = sig[slot * W32 + (site >> 5)];
+        const uint32_t bit = (word[c] >> (site & 31)) & 1u;
+        const R *rp = Q + (size_t)((int)bit * N + site) * row_reals;
+        const R a0 = __ldg(A0 + site);
+        dA[c] = bit ? -a0 : a0;
+        R acc = R(0);
+        V prod = one;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const V4 q = V4::ld(rp + 4 * L * p);  // lo = (Re q_j0, Re q_j1), hi = (Im q_j0, Im q_j1)
+          const V t = P::mul(Zi[c][p], q.hi);
+          const V nr = P::fma(Zr[c][p], q.lo, neg2_(t));
+          const V u = P::mul(Zi[c][p], q.lo);
+          const V ni = P::fma(Zr[c][p], q.hi, u);
+          if constexpr (MODE == 0) {
+            nZr[c][p] = nr;
+            nZi[c][p] = ni;
+          } else {
+            Zr[c][p] = nr;
+            Zi[c][p] = ni;
+          }
+          const V aa = add2_(nr, one);
+          V m = P::mul(aa, aa);
+          m = P::fma(ni, ni, m);
+          prod = P::mul(prod, m);
+          if (((p + 1) % GL) == 0 || p == NP - 1) {
+            acc += P::lg2(prod.x * prod.y);
+            prod = one;
+          }
+        }
+        lgn[c] = acc;
+        part[c] = acc - lg[c];
+      }
+      // ---- phase 2: sums over the lane group
+#pragma unroll
+      for (int c = 0; c < C; ++c) part[c] = group_sum_fast<L>(part[c]);
+      // ---- phase 3: accept iff log2 u < log2 |psi(x')|^2 - log2 |psi(x)|^2
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int slot = g * C + c;
+        const bool acc = (logu[c] < part[c] + dA[c]) && (chain0 + slot < a.n_chains);
+        if (acc) {
+          if constexpr (MODE == 0) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              Zr[c][p] = nZr[c][p];
+              Zi[c][p] = nZi[c][p];
+            }
+          }
+          lg[c] = lgn[c];
+          if (l == 0) {
+            sig[slot * W32 + (sitec[c] >> 5)] = word[c] ^ (1u << (sitec[c] & 31));
+            ++n_acc;
+          }
+        } else if constexpr (MODE == 1) {
+          // rejected: multiply back by the inverse row (the row of the opposite flip at the same site)
+          const uint32_t nbit = ((word[c] >> (sitec[c] & 31)) & 1u) ^ 1u;
+          const R *rp = Q + (size_t)((int)nbit * N + sitec[c]) * row_reals;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const V4 q = V4::ld(rp + 4 * L * p);
+            const V t = P::mul(Zi[c][p], q.hi);
+            const V nr = P::fma(Zr[c][p], q.lo, neg2_(t));
+            const V u = P::mul(Zi[c][p], q.lo);
+            Zi[c][p] = P::fma(Zr[c][p], q.hi, u);
+            Zr[c][p] = nr;
+          }
+        }
+      }
+      __syncwarp();
+
+      if (--until_emit == 0) {
+        until_emit = a.sweep_size;
+        if (sweep >= a.n_discard) {
+          const int ts = sweep - a.n_discard;
+          for (int idx = lane; idx < NCH * W32; idx += 32) {
+            const int slot = idx / W32, w32 = idx - slot * W32;
+            const int64_t ch = chain0 + slot;
+            if (ch < a.n_chains) a.samples[(ch * a.chain_length + ts) * W32 + w32] = sig[idx];
+          }
+        }
+        ++sweep;
+      }
     }
   }
   for (int idx = lane; idx < NCH * W32; idx += 32) {
@@ -366,7 +408,321 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDe
   }
 }
 
-template <typename R, int L, int NP, int C, int GL, int MB>
+// ------------------------------------------------------------------------------------------------------------
+// One chain per warp (L = 32), software-pipelined, copy-free.  The hot form of the multiplicative sampler.
+//   * two register images of z: the multiply phase reads one and writes the other, an accepted move just
+//     switches which one is current (no copy on accept, no multiply-back on reject);
+//   * the q row of step s + 1 is requested right after the multiply phase of step s (the site sequence comes from
+//     the RNG alone; the spin at that site is known unless step s flips the very same site, in which case the
+//     prefetched row is inverted in place), so its L1 / L2 latency overlaps the logarithm - reduction -
+//     decision tail of step s;
+//   * a batch of 128 steps of random numbers (log2 u, proposal site, A_i) is staged in shared memory by one
+//     Philox call per lane, each step reads its three words with a broadcast LDS;
+//   * the multiply phase is written stage by stage over the NP independent pairs, products combined as trees.
+// Random numbers -> steps exactly as in sample_plain_kernel / sample_ratio_kernel.
+// Acceptance test of one chain: accept iff sum over the warp of `part` exceeds thr = log2 u - A.
+// Single precision: the addends go through one integer REDUX as 2^-20 fixed point (a butterfly is five dependent
+// shuffle + add rounds on the critical path of every step) and the threshold is compared as an integer; an addend
+// outside +-60 (a hidden unit sitting exactly on a node of cosh: |1 + z|^2 underflows) saturates there, where the
+// outcome no longer depends on it (log2 u >= -25).  Double precision: butterfly sum, floating compare.
+template <typename R>
+struct WarpDecide;
+template <>
+struct WarpDecide<float> {
+  using T = int;
+  static __device__ __forceinline__ T threshold(float thr) { return __float2int_rd(thr * 1048576.0f); }
+  static __device__ __forceinline__ bool accept(float part, T thr) {
+    const int v = __float2int_rn(fminf(fmaxf(part, -60.0f), 60.0f) * 1048576.0f);
+    return __reduce_add_sync(0xffffffffu, v) > thr;
+  }
+};
+template <>
+struct WarpDecide<double> {
+  using T = double;
+  static __device__ __forceinline__ T threshold(double thr) { return thr; }
+  static __device__ __forceinline__ bool accept(double part, T thr) { return group_sum<32>(part) > thr; }
+};
+
+// WR: configuration words kept in registers (N <= 32 WR).
+template <typename R, int NP, int GL, int MB, int WR>
+__global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(NetDev<R> net, const R *ws,
+                                                                                 const R s0, const R s1, SampArgs a) {
+  using P = P2<R>;
+  using V = typename P::V;
+  using V4 = V4T<R>;
+  using D = WarpDecide<R>;
+  constexpr int L = 32;
+  constexpr int SB = 128;                 // MH steps per RNG batch: 32 lanes x one Philox block of 4
+  constexpr int NG = (NP + GL - 1) / GL;  // logarithms per step
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  if (!samp_window_ok(a)) return;
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = lane;
+  constexpr size_t per_warp = (size_t)WR * 4 + (size_t)SB * (2 * sizeof(R) + 4);
+  unsigned char *base = pipe_smem + (size_t)warp * per_warp;
+  R *s_lu = reinterpret_cast<R *>(base);                   // [SB] log2 u
+  R *s_a0 = s_lu + SB;                                     // [SB] A_site
+  int *s_site = reinterpret_cast<int *>(s_a0 + SB);        // [SB] proposal site
+  uint32_t *sig = reinterpret_cast<uint32_t *>(s_site + SB);  // [WR] configuration, synchronised once per sweep
+  const int64_t chain = (int64_t)blockIdx.x * SAMP_WARPS + warp;  // local chain of this warp
+  if (chain >= a.n_chains) return;
+  const int row_reals = 4 * NP * L;  // reals per (table, site) row
+  const R *Q = ws + 4 * l;
+  const R *A0 = ws + (size_t)8 * N * NP * L;
+  const V one = P::mk(R(1), R(1));
+
+  // ---- configuration: every lane holds all words
+  uint32_t sg[WR];
+#pragma unroll
+  for (int w = 0; w < WR; ++w) {
+    uint32_t v = 0;
+    if (w < W32) {
+      if (a.init_random) {
+        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + chain), (uint32_t)TAG_INIT};
+        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+      } else {
+        v = a.chain_state[chain * W32 + w];
+      }
+      const int nb = N - 32 * w;
+      if (nb < 32) v &= (1u << nb) - 1u;
+    }
+    sg[w] = v;
+  }
+  auto spin_bit = [&](int st) -> uint32_t {
+    uint32_t v = sg[0];
+#pragma unroll
+    for (int w = 1; w < WR; ++w) v = ((st >> 5) == w) ? sg[w] : v;
+    return (v >> (st & 31)) & 1u;
+  };
+  auto sync_sig = [&]() {
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int w = 0; w < WR; ++w) sig[w] = sg[w];
+    }
+    __syncwarp();
+  };
+
+  const int n_sweeps = a.n_discard + a.chain_length;
+  const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));
+  const uint64_t batch0 = a.step_offset - phase;
+  const bool shared_sites = (a.site_mode == 0);
+  const uint32_t chid = (uint32_t)(a.chain_offset + chain);
+
+  // stage the random numbers of the batch that starts `pos0` steps after batch0 (pos0 a multiple of SB)
+  auto refill = [&](uint32_t pos0) {
+    const uint64_t blk = ((batch0 + (uint64_t)pos0) >> 2) + (uint64_t)lane;
+    u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), chid, (uint32_t)TAG_UNIFORM};
+    const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
+    u32x4 rsite;
+    if (shared_sites) {
+      u32x4 c2 = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
+      rsite = philox4x32_10(c2, a.k0, a.k1);
+    } else {
+      ctr.w = (uint32_t)TAG_SITE_CHAIN;
+      rsite = philox4x32_10(ctr, a.k0, a.k1);
+    }
+    __syncwarp();
+    const int i0 = (int)__umulhi(rsite.x, (uint32_t)N), i1 = (int)__umulhi(rsite.y, (uint32_t)N);
+    const int i2 = (int)__umulhi(rsite.z, (uint32_t)N), i3 = (int)__umulhi(rsite.w, (uint32_t)N);
+    s_lu[4 * lane + 0] = SMath<R>::log2u(ru.x);
+    s_lu[4 * lane + 1] = SMath<R>::log2u(ru.y);
+    s_lu[4 * lane + 2] = SMath<R>::log2u(ru.z);
+    s_lu[4 * lane + 3] = SMath<R>::log2u(ru.w);
+    s_site[4 * lane + 0] = i0;
+    s_site[4 * lane + 1] = i1;
+    s_site[4 * lane + 2] = i2;
+    s_site[4 * lane + 3] = i3;
+    s_a0[4 * lane + 0] = __ldg(A0 + i0);
+    s_a0[4 * lane + 1] = __ldg(A0 + i1);
+    s_a0[4 * lane + 2] = __ldg(A0 + i2);
+    s_a0[4 * lane + 3] = __ldg(A0 + i3);
+    __syncwarp();
+  };
+
+  V ZAr[NP], ZAi[NP], ZBr[NP], ZBi[NP];
+  V4 row[NP];
+  R lg = R(0);
+  unsigned n_acc = 0, cur = 0;
+
+  // ---- prologue: random numbers and row of step 0
+  refill(0);
+  int site = s_site[phase];
+  uint32_t bit = spin_bit(site);
+  R thr_r;
+  {
+    const R a0 = s_a0[phase];
+    thr_r = s_lu[phase] - (bit ? -a0 : a0);
+    const R *rp = Q + (size_t)((int)bit * N + site) * row_reals;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) row[p] = V4::ld(rp + 4 * L * p);
+  }
+  typename D::T thr = D::threshold(thr_r);
+
+  // multiply phase: zo = zi * row, returns this lane's sum_j log2 |1 + zo_j|^2
+  auto multiply = [&](const V (&zir)[NP], const V (&zii)[NP], V (&zor)[NP], V (&zoi)[NP]) -> R {
+    V t[NP], u[NP], m[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      t[p] = P::mul(zii[p], row[p].hi);
+      u[p] = P::mul(zii[p], row[p].lo);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      zor[p] = P::fma(zir[p], row[p].lo, neg2_(t[p]));
+      zoi[p] = P::fma(zir[p], row[p].hi, u[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) m[p] = add2_(zor[p], one);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) m[p] = P::mul(m[p], m[p]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) m[p] = P::fma(zoi[p], zoi[p], m[p]);
+#pragma unroll
+    for (int st = 1; st < GL; st <<= 1)
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        if ((p % GL) % (2 * st) == 0 && (p % GL) + st < GL && p + st < NP) m[p] = P::mul(m[p], m[p + st]);
+    R acc = R(0);
+#pragma unroll
+    for (int gq = 0; gq < NG; ++gq) {
+      const R lv = P::lg2(m[gq * GL].x * m[gq * GL].y);
+      acc = gq == 0 ? lv : acc + lv;
+    }
+    return acc;
+  };
+
+  uint32_t s = 0;  // steps done
+  for (int sweep = 0; sweep < n_sweeps; ++sweep) {
+    if ((sweep % RATIO_REFRESH) == 0) {
+      // ---- theta from scratch (pairs of units), then z = exp(-2 theta) into image A; padded units carry z = 0
+      sync_sig();
+      cur = 0;
+      const V *cW = reinterpret_cast<const V *>(net.W);
+      const V *cb = reinterpret_cast<const V *>(net.b);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(R(0), R(0));
+        const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(R(0), R(0));
+        ZAr[p] = P::mk(b0.x, b1.x);
+        ZAi[p] = P::mk(b0.y, b1.y);
+      }
+      for (int i = 0; i < N; ++i) {
+        const R xv = ((sig[i >> 5] >> (i & 31)) & 1u) ? s1 : s0;
+        const V xx = P::mk(xv, xv);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int j0 = 2 * L * p + l, j1 = j0 + L;
+          const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(R(0), R(0));
+          const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(R(0), R(0));
+          ZAr[p] = P::fma(xx, P::mk(w0.x, w1.x), ZAr[p]);
+          ZAi[p] = P::fma(xx, P::mk(w0.y, w1.y), ZAi[p]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        R e0 = exp_(R(-2) * ZAr[p].x), e1 = exp_(R(-2) * ZAr[p].y);
+        R sn0, cs0, sn1, cs1;
+        sincos_(R(-2) * ZAi[p].x, &sn0, &cs0);
+        sincos_(R(-2) * ZAi[p].y, &sn1, &cs1);
+        if (j0 >= M) e0 = R(0);
+        if (j1 >= M) e1 = R(0);
+        ZAr[p] = P::mk(e0 * cs0, e1 * cs1);
+        ZAi[p] = P::mk(e0 * sn0, e1 * sn1);
+      }
+      R acc = R(0);
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq) {
+        V prod = one;
+#pragma unroll
+        for (int p = gq * GL; p < (gq + 1) * GL && p < NP; ++p) {
+          const V aa = add2_(ZAr[p], one);
+          V m = P::mul(aa, aa);
+          m = P::fma(ZAi[p], ZAi[p], m);
+          prod = P::mul(prod, m);
+        }
+        acc += P::lg2(prod.x * prod.y);
+      }
+      lg = acc;
+    }
+
+    for (int k = 0; k < a.sweep_size; ++k, ++s) {
+      // ---- random numbers of step s + 1 (harmless one step past the end); address of its row
+      const uint32_t npos = s + 1 + phase;
+      const int ntb = (int)(npos & (SB - 1));
+      if (ntb == 0) refill(npos);
+      const int nsite = s_site[ntb];
+      const R nlogu = s_lu[ntb], na0 = s_a0[ntb];
+      uint32_t nbit = spin_bit(nsite);
+      const R *nrp = Q + (size_t)((int)nbit * N + nsite) * row_reals;
+      R nthr_r = nlogu - (nbit ? -na0 : na0);
+
+      // ---- proposal z' = z q into the other image
+      R lgn;
+      if (cur == 0)
+        lgn = multiply(ZAr, ZAi, ZBr, ZBi);
+      else
+        lgn = multiply(ZBr, ZBi, ZAr, ZAi);
+
+      // ---- request the row of step s + 1: its latency overlaps the reduction and the decision
+#pragma unroll
+      for (int p = 0; p < NP; ++p) row[p] = V4::ld(nrp + 4 * L * p);
+
+      // ---- accept iff log2 u < log2 |psi(x')|^2 - log2 |psi(x)|^2
+      if (D::accept(lgn - lg, thr)) {
+        lg = lgn;
+        cur ^= 1u;
+        ++n_acc;
+        {
+          const uint32_t msk = 1u << (site & 31);
+#pragma unroll
+          for (int w = 0; w < WR; ++w)
+            if ((site >> 5) == w) sg[w] ^= msk;
+        }
+        if (nsite == site) {
+          // the next proposal flips the same spin back: its row is the inverse of the one requested above
+          nthr_r = nlogu - (nbit ? na0 : -na0);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const V d = P::fma(row[p].hi, row[p].hi, P::mul(row[p].lo, row[p].lo));
+            const V inv = P::mk(R(1) / d.x, R(1) / d.y);
+            row[p].lo = P::mul(row[p].lo, inv);
+            row[p].hi = neg2_(P::mul(row[p].hi, inv));
+          }
+        }
+      }
+      site = nsite;
+      thr = D::threshold(nthr_r);
+    }
+
+    // ---- sweep boundary: emit the configuration
+    sync_sig();
+    if (sweep >= a.n_discard && lane < W32)
+      a.samples[(chain * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sig[lane];
+  }
+  sync_sig();
+  if (lane < W32) a.chain_state[chain * W32 + lane] = sig[lane];
+  if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+}
+
+constexpr int PIPE_WR = 4;  // the pipelined kernel keeps the configuration in 4 registers: N <= 128
+
+template <typename R, int NP, int GL, int MB>
+static int launch_ratio_pipe(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
+                             cudaStream_t st) {
+  if (net->n_visible > 32 * PIPE_WR) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "pipelined sampler: N > %d", 32 * PIPE_WR);
+  const int64_t blocks = (a.n_chains + SAMP_WARPS - 1) / SAMP_WARPS;
+  const size_t smem = (size_t)SAMP_WARPS * ((size_t)PIPE_WR * 4 + 128 * (2 * sizeof(R) + 4));
+  sample_ratio_pipe_kernel<R, NP, GL, MB, PIPE_WR><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
+      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+template <typename R, int L, int NP, int C, int GL, int MB, int MODE = 1>
 static int launch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws, cudaStream_t st) {
   constexpr int NCH = (32 / L) * C;
   const int W32 = (net->n_visible + 31) >> 5;
@@ -374,11 +730,11 @@ static int launch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &
   const int64_t blocks = (warps + SAMP_WARPS - 1) / SAMP_WARPS;
   const size_t smem = (size_t)SAMP_WARPS * NCH * W32 * sizeof(uint32_t);
   if (smem > 48 * 1024) {
-    cudaError_t rc = cudaFuncSetAttribute(sample_ratio_kernel<R, L, NP, C, GL, MB>,
+    cudaError_t rc = cudaFuncSetAttribute(sample_ratio_kernel<R, L, NP, C, GL, MB, MODE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   }
-  sample_ratio_kernel<R, L, NP, C, GL, MB><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
+  sample_ratio_kernel<R, L, NP, C, GL, MB, MODE><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
       make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

@@ -10,19 +10,33 @@ namespace nkfb {
 #define NKFB_CAT(a, b, c) NKFB_CAT_(a, b, c)
 #define NKFB_FN NKFB_CAT(dispatch_ratio_, NKFB_RN, NKFB_L)
 
-// chains per lane group and minimum resident CTAs per SM: the state is 4 NP C registers (z) plus as many for
-// the proposal z', in units of sizeof(R) / 4
+// chains per lane group and minimum resident CTAs per SM: the state is 4 NP C registers (z) plus 4 NP for the row
+// in flight, in units of sizeof(R) / 4
 template <typename R, int NP>
 struct RatioShape {
   static constexpr bool f32 = sizeof(R) == 4;
-  static constexpr int C = f32 ? (NP <= 2 ? 4 : (NP <= 7 ? 2 : 1)) : (NP <= 2 ? 2 : 1);
-  static constexpr int MB = f32 ? (NP <= 4 ? 4 : (NP <= 7 ? 3 : (NP <= 8 ? 4 : (NP <= 12 ? 3 : 2)))) : (NP <= 4 ? 3 : 2);
+  static constexpr int C = f32 ? (NP <= 2 ? 4 : (NP <= 8 ? 2 : 1)) : (NP <= 2 ? 2 : 1);
+  static constexpr int MB = f32 ? (NP <= 7 ? 4 : (NP <= 8 ? 3 : (NP <= 12 ? 4 : 3))) : (NP <= 4 ? 3 : 2);
+};
+
+// pipelined one-chain-per-warp kernel (32 lanes, N <= 128): three register images of 4 NP words (z, z', q row)
+template <typename R, int NP>
+struct PipeShape {
+  static constexpr bool f32 = sizeof(R) == 4;
+  static constexpr int MB = f32 ? (NP <= 7 ? 4 : (NP <= 9 ? 3 : 2)) : (NP <= 3 ? 4 : (NP <= 4 ? 3 : 2));
 };
 
 template <int NP>
 static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_one, const void *ws, cudaStream_t st) {
   using S = RatioShape<NKFB_RT, NP>;
   constexpr int GW = NP < 4 ? NP : 4;
+#if NKFB_L == 32
+  if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOPIPE")) {
+    constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
+    if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, a, ws, st);
+    return launch_ratio_pipe<NKFB_RT, NP, GW, PMB>(h, net, a, ws, st);
+  }
+#endif
   if (gl_one) return launch_ratio<NKFB_RT, NKFB_L, NP, S::C, 1, S::MB>(h, net, a, ws, st);
   return launch_ratio<NKFB_RT, NKFB_L, NP, S::C, GW, S::MB>(h, net, a, ws, st);
 }
@@ -55,15 +69,24 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
     const char *v = getenv("NKFB_RATIO_VARIANT");
     const int iv = v ? atoi(v) : 0;
     switch (iv) {
-      case 1: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 3>(h, net, a, ws, st);
-      case 2: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 4>(h, net, a, ws, st);
-      case 3: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 4>(h, net, a, ws, st);
-      case 4: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 5>(h, net, a, ws, st);
-      case 5: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 6>(h, net, a, ws, st);
-      case 6: return launch_ratio<NKFB_RT, 32, 7, 2, 7, 3>(h, net, a, ws, st);
-      case 7: return launch_ratio<NKFB_RT, 32, 7, 2, 2, 3>(h, net, a, ws, st);
-      case 8: return launch_ratio<NKFB_RT, 32, 7, 3, 4, 2>(h, net, a, ws, st);
-      case 9: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 2>(h, net, a, ws, st);
+      case 1: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 3, 0>(h, net, a, ws, st);
+      case 2: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 4, 1>(h, net, a, ws, st);
+      case 3: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 4, 1>(h, net, a, ws, st);
+      case 4: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 5, 1>(h, net, a, ws, st);
+      case 5: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 6, 1>(h, net, a, ws, st);
+      case 6: return launch_ratio<NKFB_RT, 32, 7, 2, 7, 4, 1>(h, net, a, ws, st);
+      case 7: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 3, 1>(h, net, a, ws, st);
+      case 8: return launch_ratio<NKFB_RT, 32, 7, 3, 4, 3, 1>(h, net, a, ws, st);
+      case 9: return launch_ratio<NKFB_RT, 32, 7, 1, 4, 5, 0>(h, net, a, ws, st);
+      case 10: return launch_ratio<NKFB_RT, 32, 7, 2, 4, 5, 1>(h, net, a, ws, st);
+      case 11: return launch_ratio<NKFB_RT, 32, 7, 4, 4, 2, 1>(h, net, a, ws, st);
+      case 12: return launch_ratio<NKFB_RT, 32, 7, 3, 4, 4, 1>(h, net, a, ws, st);
+      case 13: return launch_ratio<NKFB_RT, 32, 7, 1, 7, 6, 1>(h, net, a, ws, st);
+      case 20: return launch_ratio_pipe<NKFB_RT, 7, 4, 4>(h, net, a, ws, st);
+      case 21: return launch_ratio_pipe<NKFB_RT, 7, 4, 3>(h, net, a, ws, st);
+      case 22: return launch_ratio_pipe<NKFB_RT, 7, 4, 5>(h, net, a, ws, st);
+      case 23: return launch_ratio_pipe<NKFB_RT, 7, 7, 4>(h, net, a, ws, st);
+      case 24: return launch_ratio_pipe<NKFB_RT, 7, 2, 4>(h, net, a, ws, st);
       default: break;
     }
   }

@@ -24,6 +24,7 @@ mufu = h.microbench(0, 2048)
 # variants >= 100: multiplicative sampler (NKFB_RATIO_VARIANT = v - 100); below: additive sampler variants
 print(f"MUFU.EX2 {mufu / 1e12:.3f} T/s  FFMA {h.microbench(3, 4096) / 1e12:.2f} T/s  "
       f"FFMA2 {h.microbench(5, 4096) / 1e12:.2f} T FMA/s", flush=True)
+ref_out = None
 for v in variants:
     if v >= 100:
         os.environ["NKFB_SAMPLER_ALGO"] = "2"
@@ -45,3 +46,12 @@ for v in variants:
     print(f"variant {v}: {t:.3f} ms  {evals / t / 1e6:.1f} G evals/s  frac of MUFU roofline "
           f"{evals * 2.25 / (t * 1e-3) / mufu:.3f}  acc {nacc.item() / (4 * evals / M):.4f}", flush=True)
     nacc.zero_()
+    # same random numbers in every variant: all but a few chains must emit identical samples
+    state.zero_()
+    h.sample(net, state, w["chain_length"], 5, N, 7, (-1.0, 1.0), init_random=True, out=out)
+    torch.cuda.synchronize()
+    if ref_out is None:
+        ref_out = out.clone()
+    else:
+        same = (out.view(out.shape[0], -1) == ref_out.view(out.shape[0], -1)).all(dim=1).float().mean().item()
+        print(f"    chains identical to the first variant: {same:.4f}", flush=True)
