@@ -250,7 +250,9 @@ int dispatch_ratio_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, 
 
 // workspace = [ratio-sampler tables (sampler_ratio.cuh) | pre-scaled parameters of the additive sampler]
 static size_t plain_ws_offset_reals(int N, int M) { return (ratio_ws_reals_max(N, M) + 63) & ~(size_t)63; }
-static size_t sampler_ws_total_reals(int N, int M) { return plain_ws_offset_reals(N, M) + sampler_ws_reals(N, M); }
+static size_t seq_ws_offset_reals(int N, int M) { return (plain_ws_offset_reals(N, M) + sampler_ws_reals(N, M) + 63) & ~(size_t)63; }
+// site table of the CTA-synchronous kernel: SITE_SEQ_CAP ints + SITE_SEQ_CAP reals
+static size_t sampler_ws_total_reals(int N, int M) { return seq_ws_offset_reals(N, M) + 2 * (size_t)SITE_SEQ_CAP; }
 
 // lane-group width of the multiplicative sampler: least padded work among the instantiated shapes (<= 8 pairs per
 // lane, <= 16 on 32 lanes in single precision); 0 if the shape is not covered
@@ -293,6 +295,23 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
     NKFB_LAUNCHED(h);
   }
   a.xbound = reinterpret_cast<const float *>((const char *)ws + b_off * rsz);
+  // shared site sequence on full warps: table of the proposal sites of this call for the CTA-synchronous kernel
+  const uint64_t n_steps = (uint64_t)(a.n_discard + a.chain_length) * (uint64_t)a.sweep_size;
+  if (a.site_mode == 0 && L == 32 && NP <= 8 && N <= 32 * PIPE_WR && n_steps > 0 && n_steps <= (uint64_t)SITE_SEQ_CAP) {
+    char *seq = (char *)ws + seq_ws_offset_reals(N, M) * rsz;
+    int *site_seq = reinterpret_cast<int *>(seq);
+    void *a0_seq = seq + (size_t)SITE_SEQ_CAP * 4;
+    const unsigned grid = (unsigned)((n_steps + 255) / 256);
+    if (f32)
+      prep_site_seq<float><<<grid, 256, 0, st>>>((const float *)ws + a0_off, N, a.k0, a.k1, a.step_offset,
+                                                 (uint32_t)n_steps, site_seq, (float *)a0_seq);
+    else
+      prep_site_seq<double><<<grid, 256, 0, st>>>((const double *)ws + a0_off, N, a.k0, a.k1, a.step_offset,
+                                                  (uint32_t)n_steps, site_seq, (double *)a0_seq);
+    NKFB_LAUNCHED(h);
+    a.site_seq = site_seq;
+    a.a0_seq = a0_seq;
+  }
   const int GW = NP < 4 ? NP : 4;
   const float x1 = ratio_xmax(GW), x2 = ratio_xmax(1);
   for (int pass = 0; pass < 2; ++pass) {

@@ -21,6 +21,9 @@ struct SampArgs {
   // xlo < *xbound <= xhi, so that exactly one of the kernels launched back to back does the work
   const float *xbound;
   float xlo, xhi;
+  // site_mode 0: proposal sites / A_site of the steps of this call (prep_site_seq), or null
+  const int *site_seq;
+  const void *a0_seq;
   OpDev op;
 };
 

@@ -144,6 +144,7 @@ __device__ __forceinline__ double group_sum_fast(double v) { return group_sum<L>
 //         move is REJECTED: half the registers, no copies; z is recomputed from the configuration every
 //         RATIO_REFRESH sweeps, which bounds the rounding drift of the products (both modes).
 constexpr int RATIO_REFRESH = 32;
+constexpr int PIPE_WR_ = 4;  // configuration words kept in registers by the one-warp-per-chain kernels: N <= 128
 
 template <typename R, int L, int NP, int C, int GL, int MB, int MODE>
 __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDev<R> net, const R *ws, const R s0,
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
   if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-constexpr int PIPE_WR = 4;  // the pipelined kernel keeps the configuration in 4 registers: N <= 128
+constexpr int PIPE_WR = PIPE_WR_;
 
 template <typename R, int NP, int GL, int MB>
 static int launch_ratio_pipe(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
@@ -718,6 +719,362 @@ static int launch_ratio_pipe(nkfb_handle_t h, const nkfb_rbm_t *net, const SampA
   const size_t smem = (size_t)SAMP_WARPS * ((size_t)PIPE_WR * 4 + 128 * (2 * sizeof(R) + 4));
   sample_ratio_pipe_kernel<R, NP, GL, MB, PIPE_WR><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(
       make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-synchronous form for the shared site sequence (site_mode 0): the hot form of the multiplicative sampler.
+//
+// Every chain of the launch proposes the same site at the same step, so all chains of a CTA need the same two q
+// rows (spin up / spin down) at step s.  The CTA stages them ONCE in shared memory, a chunk of T steps at a time,
+// double-buffered with cp.async (global -> shared without registers) and one __syncthreads per chunk:
+//   * L2 / L1 traffic per chain-step drops from one 16 NP-byte-per-lane row to 1 / (chains per CTA) of two rows
+//     (the per-warp kernels re-read every row from L1 / L2: 4e11 B per launch at the north-star shape);
+//   * no per-lane row registers: a warp carries C = 2..4 chains (z only, multiplied IN PLACE; a rejected move is
+//     multiplied back by the other row of the same slot, which is the inverse), so 8..12 chains per SM
+//     sub-partition are in flight instead of 4 and their reduction / decision latencies overlap;
+//   * the site sequence and A_site come from a table written by prep_site_seq (they depend on the RNG alone).
+// Random numbers -> steps exactly as in the other plain-target kernels.
+constexpr int SITE_SEQ_CAP = 1 << 16;  // steps per call covered by the site table in the workspace
+
+template <typename R>
+__global__ void prep_site_seq(const R *A0, int N, uint32_t k0, uint32_t k1, uint64_t step_offset, uint32_t n_steps,
+                              int *site_seq, R *a0_seq) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_steps) return;
+  const uint64_t pos = step_offset + s, blk = pos >> 2;
+  u32x4 c2 = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
+  const int site = (int)__umulhi(sel4(philox4x32_10(c2, k0, k1), (int)(pos & 3)), (uint32_t)N);
+  site_seq[s] = site;
+  a0_seq[s] = A0[site];
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <typename R, int NP, int C, int GL, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1) sample_ratio_cta_kernel(NetDev<R> net, const R *ws, const R s0, const R s1,
+                                                                   SampArgs a, const int *site_seq, const R *a0_seq,
+                                                                   const int TSH) {
+  using P = P2<R>;
+  using V = typename P::V;
+  using D = WarpDecide<R>;
+  constexpr int L = 32, SB = 128, WR = PIPE_WR_;
+  constexpr int NG = (NP + GL - 1) / GL;
+  constexpr int ROW = 4 * NP * L;  // reals per (table, site) row
+  extern __shared__ __align__(16) unsigned char cta_smem[];
+  if (!samp_window_ok(a)) return;  // uniform over the grid: taken before any barrier
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int l = lane;
+  const int T = 1 << TSH;  // steps per chunk
+  R *rows = reinterpret_cast<R *>(cta_smem);                                   // [2][T][2][ROW]
+  R *s_lu = rows + (size_t)4 * T * ROW + (size_t)warp * C * SB;                // [C][SB] of this warp
+  uint32_t *sigx = reinterpret_cast<uint32_t *>(rows + (size_t)4 * T * ROW + (size_t)W * C * SB) + warp * C * WR;
+  const int64_t chain0 = ((int64_t)blockIdx.x * W + warp) * C;
+  const R *Qg = ws;  // global tables
+  const V one = P::mk(R(1), R(1));
+  // chains of this warp that exist (the others are carried along: every warp takes part in the CTA barriers)
+  const int n_valid = a.n_chains - chain0 >= C ? C : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
+
+  // ---- configurations: every lane holds all words of the C chains
+  uint32_t sg[C][WR];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int w = 0; w < WR; ++w) {
+      uint32_t v = 0;
+      if (w < W32 && c < n_valid) {
+        if (a.init_random) {
+          u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_INIT};
+          v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+        } else {
+          v = a.chain_state[(chain0 + c) * W32 + w];
+        }
+        const int nb = N - 32 * w;
+        if (nb < 32) v &= (1u << nb) - 1u;
+      }
+      sg[c][w] = v;
+    }
+  auto sync_sig = [&]() {
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int w = 0; w < WR; ++w) sigx[c * WR + w] = sg[c][w];
+    }
+    __syncwarp();
+  };
+
+  const int n_sweeps = a.n_discard + a.chain_length;
+  const uint32_t n_steps = (uint32_t)n_sweeps * (uint32_t)a.sweep_size;
+  const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));
+  const uint64_t batch0 = a.step_offset - phase;
+
+  // log2 u of the batch that starts `pos0` steps after batch0, for the C chains of this warp
+  auto refill = [&](uint32_t pos0) {
+    __syncwarp();
+    const uint64_t blk = ((batch0 + (uint64_t)pos0) >> 2) + (uint64_t)lane;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_UNIFORM};
+      const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
+      s_lu[c * SB + 4 * lane + 0] = SMath<R>::log2u(ru.x);
+      s_lu[c * SB + 4 * lane + 1] = SMath<R>::log2u(ru.y);
+      s_lu[c * SB + 4 * lane + 2] = SMath<R>::log2u(ru.z);
+      s_lu[c * SB + 4 * lane + 3] = SMath<R>::log2u(ru.w);
+    }
+    __syncwarp();
+  };
+  // request the 2 T rows of chunk qn (positions qn T .. qn T + T - 1) into buffer qn & 1
+  auto issue_rows = [&](uint32_t qn) {
+    for (int r = warp; r < 2 * T; r += W) {
+      const int tt = r >> 1, tab = r & 1;
+      const int64_t sidx = ((int64_t)qn << TSH) + tt - (int64_t)phase;
+      const uint32_t sc = sidx < 0 ? 0u : (sidx >= (int64_t)n_steps ? n_steps - 1 : (uint32_t)sidx);
+      const int st = __ldg(site_seq + sc);
+      const char *src = reinterpret_cast<const char *>(Qg + (size_t)(tab * N + st) * ROW);
+      char *dst = reinterpret_cast<char *>(rows + ((((qn & 1u) << TSH) + tt) * 2 + tab) * ROW);
+      for (int off = lane * 16; off < (int)(ROW * sizeof(R)); off += 512) cp_async16(dst + off, src + off);
+    }
+  };
+
+  V Zr[C][NP], Zi[C][NP];
+  R lg[C];
+  unsigned n_acc = 0;
+
+  // z <- z * row (in place); returns this lane's sum_j log2 |1 + z_j|^2.  rp: shared memory, lane offset applied.
+  // One group of GL pairs (one logarithm) at a time: stage by stage inside the group, which bounds the temporaries.
+  auto multiply = [&](V (&zr)[NP], V (&zi)[NP], const R *rp, bool want_log) -> R {
+    R acc = R(0);
+#pragma unroll
+    for (int gq = 0; gq < NG; ++gq) {
+      constexpr int GS = GL;
+      V qlo[GS], qhi[GS], t[GS], u[GS], m[GS];
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int p = gq * GL + i;
+        if (p < NP) {
+          const V *q = reinterpret_cast<const V *>(rp + 4 * L * p);
+          qlo[i] = q[0];
+          qhi[i] = q[1];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int p = gq * GL + i;
+        if (p < NP) {
+          t[i] = P::mul(zi[p], qhi[i]);
+          u[i] = P::mul(zi[p], qlo[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int p = gq * GL + i;
+        if (p < NP) {
+          zi[p] = P::fma(zr[p], qhi[i], u[i]);
+          zr[p] = P::fma(zr[p], qlo[i], neg2_(t[i]));
+        }
+      }
+      if (want_log) {
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = add2_(zr[gq * GL + i], one);
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = P::mul(m[i], m[i]);
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = P::fma(zi[gq * GL + i], zi[gq * GL + i], m[i]);
+#pragma unroll
+        for (int st = 1; st < GS; st <<= 1)
+#pragma unroll
+          for (int i = 0; i < GS; ++i)
+            if (i % (2 * st) == 0 && i + st < GS && gq * GL + i + st < NP) m[i] = P::mul(m[i], m[i + st]);
+        const R lv = P::lg2(m[0].x * m[0].y);
+        acc = gq == 0 ? lv : acc + lv;
+      }
+    }
+    return acc;
+  };
+
+  // ---- prologue: rows of the first two chunks, random numbers of the first batch
+  const uint32_t q0 = phase >> TSH;
+  issue_rows(q0);
+  cp_async_wait_all();
+  __syncthreads();
+  issue_rows(q0 + 1);
+  refill(0);
+  int nsite = __ldg(site_seq);
+  R na0 = __ldg(a0_seq);
+
+  uint32_t s = 0;  // steps done
+  for (int sweep = 0; sweep < n_sweeps; ++sweep) {
+    if ((sweep % RATIO_REFRESH) == 0) {
+      // ---- theta from scratch (pairs of units), then z = exp(-2 theta); padded units carry z = 0
+      sync_sig();
+      const V *cW = reinterpret_cast<const V *>(net.W);
+      const V *cb = reinterpret_cast<const V *>(net.b);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + l, j1 = j0 + L;
+        const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(R(0), R(0));
+        const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(R(0), R(0));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          Zr[c][p] = P::mk(b0.x, b1.x);
+          Zi[c][p] = P::mk(b0.y, b1.y);
+        }
+      }
+      for (int i = 0; i < N; ++i) {
+        V xx[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const R xv = ((sigx[c * WR + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+          xx[c] = P::mk(xv, xv);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int j0 = 2 * L * p + l, j1 = j0 + L;
+          const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(R(0), R(0));
+          const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(R(0), R(0));
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            Zr[c][p] = P::fma(xx[c], P::mk(w0.x, w1.x), Zr[c][p]);
+            Zi[c][p] = P::fma(xx[c], P::mk(w0.y, w1.y), Zi[c][p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int j0 = 2 * L * p + l, j1 = j0 + L;
+          R e0 = exp_(R(-2) * Zr[c][p].x), e1 = exp_(R(-2) * Zr[c][p].y);
+          R sn0, cs0, sn1, cs1;
+          sincos_(R(-2) * Zi[c][p].x, &sn0, &cs0);
+          sincos_(R(-2) * Zi[c][p].y, &sn1, &cs1);
+          if (j0 >= M) e0 = R(0);
+          if (j1 >= M) e1 = R(0);
+          Zr[c][p] = P::mk(e0 * cs0, e1 * cs1);
+          Zi[c][p] = P::mk(e0 * sn0, e1 * sn1);
+        }
+        R acc = R(0);
+#pragma unroll
+        for (int gq = 0; gq < NG; ++gq) {
+          V prod = one;
+#pragma unroll
+          for (int p = gq * GL; p < (gq + 1) * GL && p < NP; ++p) {
+            const V aa = add2_(Zr[c][p], one);
+            V m = P::mul(aa, aa);
+            m = P::fma(Zi[c][p], Zi[c][p], m);
+            prod = P::mul(prod, m);
+          }
+          acc += P::lg2(prod.x * prod.y);
+        }
+        lg[c] = acc;
+      }
+    }
+
+    for (int k = 0; k < a.sweep_size; ++k, ++s) {
+      const uint32_t pos = s + phase;
+      const int tb = (int)(pos & (SB - 1));
+      if (tb == 0 && s != 0) refill(pos);
+      const int site = nsite;
+      const R a0 = na0;
+      {
+        const uint32_t sn = s + 1 < n_steps ? s + 1 : s;
+        nsite = __ldg(site_seq + sn);
+        na0 = __ldg(a0_seq + sn);
+      }
+      const R *slot = rows + (pos & (uint32_t)(2 * T - 1)) * (2 * ROW) + 4 * l;  // [chunk parity][step in chunk]
+      const uint32_t msk = 1u << (site & 31);
+      const int wsel = site >> 5;
+
+      uint32_t bit[C];
+      R lgn[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        uint32_t v = sg[c][0];
+#pragma unroll
+        for (int w = 1; w < WR; ++w) v = (wsel == w) ? sg[c][w] : v;
+        bit[c] = (v >> (site & 31)) & 1u;
+        lgn[c] = multiply(Zr[c], Zi[c], slot + bit[c] * ROW, true);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const typename D::T thr = D::threshold(s_lu[c * SB + tb] - (bit[c] ? -a0 : a0));
+        if (D::accept(lgn[c] - lg[c], thr) && c < n_valid) {
+          lg[c] = lgn[c];
+          ++n_acc;
+#pragma unroll
+          for (int w = 0; w < WR; ++w) sg[c][w] ^= (wsel == w) ? msk : 0u;
+        } else {
+          // rejected: multiply back by the other row of the slot (the inverse of the one just applied)
+          multiply(Zr[c], Zi[c], slot + (bit[c] ^ 1u) * ROW, false);
+        }
+      }
+      if ((pos & (uint32_t)(T - 1)) == (uint32_t)(T - 1)) {
+        // end of a chunk: the next one has landed everywhere, this one is free for the one after it
+        cp_async_wait_all();
+        __syncthreads();
+        issue_rows((pos >> TSH) + 2);
+      }
+    }
+
+    // ---- sweep boundary: emit the configurations
+    sync_sig();
+    if (sweep >= a.n_discard && lane < W32) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (c < n_valid)
+          a.samples[((chain0 + c) * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sigx[c * WR + lane];
+    }
+  }
+  cp_async_wait_all();
+  sync_sig();
+  if (lane < W32) {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (c < n_valid) a.chain_state[(chain0 + c) * W32 + lane] = sigx[c * WR + lane];
+  }
+  if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+}
+
+// warps per CTA and log2 of the chunk length: `maxw` warps (one CTA per SM) for large launches; for small ones
+// (multi-GPU shards) enough CTAs to touch every SM, with shorter chunks so that several CTAs share an SM.
+inline void ratio_cta_shape(int64_t n_chains, int C, int sm_count, int maxw, int *W, int *TSH) {
+  int64_t w = (n_chains + (int64_t)C * sm_count - 1) / ((int64_t)C * sm_count);
+  if (w > maxw) w = maxw;
+  if (w < 2) w = 2;
+  *W = (int)w;
+  *TSH = w >= 10 ? 3 : 2;
+}
+template <typename R>
+inline size_t ratio_cta_smem(int NP, int C, int W, int TSH) {
+  return ((size_t)4 * (1 << TSH) * 4 * NP * 32 + (size_t)W * C * 128) * sizeof(R) + (size_t)W * C * PIPE_WR_ * 4;
+}
+
+template <typename R, int NP, int C, int GL, int MAXW = 16>
+static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
+                            const int *site_seq, const R *a0_seq, cudaStream_t st) {
+  int W, TSH;
+  ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
+  if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning override
+  const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH);
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
+  const int64_t blocks = (a.n_chains + (int64_t)C * W - 1) / ((int64_t)C * W);
+  sample_ratio_cta_kernel<R, NP, C, GL, MAXW><<<(unsigned)blocks, W * 32, smem, st>>>(
+      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a, site_seq, a0_seq, TSH);
   NKFB_LAUNCHED(h);
   return NKFB_OK;
 }

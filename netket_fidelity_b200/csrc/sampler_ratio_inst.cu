@@ -31,6 +31,15 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
   using S = RatioShape<NKFB_RT, NP>;
   constexpr int GW = NP < 4 ? NP : 4;
 #if NKFB_L == 32
+  if constexpr (NP <= 8) {
+    if (a.site_seq != nullptr && net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOCTA")) {
+      // shared site sequence: CTA-synchronous kernel, C chains per warp (z only: 4 NP words per chain)
+      constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
+      if (gl_one)
+        return launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      return launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+    }
+  }
   if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOPIPE")) {
     constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
     if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, a, ws, st);
@@ -82,6 +91,16 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
       case 11: return launch_ratio<NKFB_RT, 32, 7, 4, 4, 2, 1>(h, net, a, ws, st);
       case 12: return launch_ratio<NKFB_RT, 32, 7, 3, 4, 4, 1>(h, net, a, ws, st);
       case 13: return launch_ratio<NKFB_RT, 32, 7, 1, 7, 6, 1>(h, net, a, ws, st);
+      case 30: return launch_ratio_cta<NKFB_RT, 7, 3, 4>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 31: return launch_ratio_cta<NKFB_RT, 7, 2, 4>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 32: return launch_ratio_cta<NKFB_RT, 7, 4, 4>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 33: return launch_ratio_cta<NKFB_RT, 7, 3, 7>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 34: return launch_ratio_cta<NKFB_RT, 7, 3, 4, 12>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 35: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 8>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 36: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 10>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 37: return launch_ratio_cta<NKFB_RT, 7, 3, 4, 14>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 38: return launch_ratio_cta<NKFB_RT, 7, 2, 4, 12>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 39: return launch_ratio_cta<NKFB_RT, 7, 5, 4, 8>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 20: return launch_ratio_pipe<NKFB_RT, 7, 4, 4>(h, net, a, ws, st);
       case 21: return launch_ratio_pipe<NKFB_RT, 7, 4, 3>(h, net, a, ws, st);
       case 22: return launch_ratio_pipe<NKFB_RT, 7, 4, 5>(h, net, a, ws, st);

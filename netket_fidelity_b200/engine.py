@@ -19,6 +19,8 @@ as plumbing for the two all-reduces.
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native as nv
@@ -84,6 +86,7 @@ class InfidelityStep:
         # the two chain families are sampled on two streams so that the tail of one launch (a partial last
         # wave of CTAs) overlaps the other launch; each has its own scratch for the pre-scaled parameters
         self.side_stream = torch.cuda.Stream(device=dev)
+        self.single_stream = os.environ.get("NKFB_SINGLE_STREAM", "0") == "1"
         self.ws_psi = self.ws_phi = None
         self.steps_done = 0
         self.initialised = False
@@ -98,18 +101,21 @@ class InfidelityStep:
         if self.ws_psi is None:
             self.ws_psi, self.ws_phi = self.h.sample_workspace(psi), self.h.sample_workspace(phi)
         main = torch.cuda.current_stream(self.dev)
-        self.side_stream.wait_stream(main)
+        side = main if self.single_stream else self.side_stream
+        if not self.single_stream:
+            self.side_stream.wait_stream(main)
         # the two families use disjoint global chain ids: psi [0, n_chains), phi [n_chains, 2 n_chains)
         self.h.sample(psi, self.state_psi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
                       cfg.local_states, op=None, chain_offset=self.chain_offset, step_offset=step_offset,
                       site_mode=cfg.site_mode, init_random=init, n_accepted=self.n_accepted[0:1], out=self.sigma,
                       workspace=self.ws_psi)
-        with torch.cuda.stream(self.side_stream):
+        with torch.cuda.stream(side):
             self.h.sample(phi, self.state_phi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
                           cfg.local_states, op=self.op_target, chain_offset=cfg.n_chains + self.chain_offset,
                           step_offset=step_offset, site_mode=cfg.site_mode, init_random=init,
                           n_accepted=self.n_accepted[1:2], out=self.eta, workspace=self.ws_phi)
-        main.wait_stream(self.side_stream)
+        if not self.single_stream:
+            main.wait_stream(self.side_stream)
         self.initialised = True
         self.steps_done += 1
 

@@ -37,7 +37,7 @@ for v in variants:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h.sample(net, state, w["chain_length"], 5, N, 7, (-1.0, 1.0), init_random=(rep == 0), out=out,
-                 n_accepted=nacc)
+                 n_accepted=nacc, step_offset=int(os.environ.get("TUNE_STEP_OFFSET", "0")) * rep)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
