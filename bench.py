@@ -264,16 +264,18 @@ def run_b200(args):
     line = None
     if rank == 0:
         hbm_gbs, _, how = read_peaks()
-        # roofline of the dominant kernel (the sampler): SFU (MUFU) pipe.
-        mufu = max(h.microbench(0, 2048), 1.0)          # MUFU.EX2 ops/s measured on this GPU, this run
-        mufu_cos = max(h.microbench(1, 2048), 1.0)
+        # roofline of the dominant kernel (the multiplicative sampler, sampler_ratio.cuh): FP32 pipe.
+        # Per hidden unit and proposal: complex multiply z q (4), 1 + z' (1), |.|^2 (2), running product (1) =
+        # 8 FP32-pipe operations, issued as packed FFMA2 / FMUL2 / FADD2 (two per instruction).
+        ffma2 = max(h.microbench(5, 4096), 1.0)         # FMA/s through FFMA2 measured on this GPU, this run
         ffma = max(h.microbench(3, 4096), 1.0)
+        mufu = max(h.microbench(0, 2048), 1.0)
         sweeps = 5 + w["chain_length"]
-        evals_per_launch = eng.local_chains * sweeps * N * M          # Re-logcosh evaluations, one family
+        evals_per_launch = eng.local_chains * sweeps * N * M          # hidden-unit updates, one family
         t_launch = samp_ms * 1e-3 / 2
         achieved = evals_per_launch / t_launch
-        mufu_per_eval = 2.25                                          # ex2 + cos + lg2/4
-        peak = mufu / mufu_per_eval
+        ops_per_eval = 8.0
+        peak = ffma2 / ops_per_eval
         bytes_per_launch = eng.local_chains * w["chain_length"] * eng.W32 * 4 + N * M * 8
         _, bf16_peak, _ = read_peaks()
         S_loc = eng.S_local
@@ -300,20 +302,22 @@ def run_b200(args):
             "e2e": {"value": S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "sfu", "kernel": "sample_plain_kernel", "achieved": achieved / 1e9,
-                         "peak": peak / 1e9, "unit": "G logcosh-evals/s", "frac": achieved / peak,
-                         "traffic": 642048,
-                         "note": (f"the dominant kernel is MUFU-bound, neither HBM- nor tensor-bound: algorithmic work = "
-                                  f"{evals_per_launch:.3e} Re-logcosh evals per launch (chains x sweeps x N x M) at "
-                                  f"{mufu_per_eval} MUFU each; peak = MUFU.EX2 rate measured by nkfb_microbench in this "
-                                  f"run ({mufu / 1e12:.3f} T op/s; MUFU.COS {mufu_cos / 1e12:.3f}; FFMA {ffma / 1e12:.2f} T/s) "
-                                  f"/ {mufu_per_eval}; avg launch {t_launch * 1e3:.3f} ms; sampler share of step "
-                                  f"{samp_ms / (ms_total / args.steps):.3f}"),
+            "roofline": {"bound": "fp32", "kernel": "sample_ratio_cta_kernel", "achieved": achieved / 1e9,
+                         "peak": peak / 1e9, "unit": "G hidden-unit updates/s", "frac": achieved / peak,
+                         "traffic": 1451776,
+                         "note": (f"the dominant kernel is bound by the FP32 pipe, neither HBM nor tensor: algorithmic work = "
+                                  f"{evals_per_launch:.3e} hidden-unit updates per launch (chains x sweeps x N x M) at "
+                                  f"{ops_per_eval:.0f} FP32-pipe operations each (complex multiply, |1+z|^2, product; no "
+                                  f"transcendental per unit); peak = FFMA2 rate measured by nkfb_microbench in this run "
+                                  f"({ffma2 / 1e12:.2f} T FMA/s; scalar FFMA {ffma / 1e12:.2f} T/s; MUFU.EX2 "
+                                  f"{mufu / 1e12:.3f} T/s) / {ops_per_eval:.0f}; avg launch {t_launch * 1e3:.3f} ms (two "
+                                  f"launches share the GPU on two streams: half of the time both take); sampler share "
+                                  f"of step {samp_ms / (ms_total / args.steps):.3f}"),
                          "hbm_view": {"bound": "hbm", "achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_gbs,
                                       "unit": "GB/s", "frac": bytes_per_launch / t_launch / 1e9 / hbm_gbs,
                                       "peak_source": how},
                          "traffic_note": "dram__bytes_read+write of one sampler launch from profiles/r01_ncu_top_kernels.md "
-                                         "(0.63 MB read + 12 KB written: parameters and packed samples stay in L2)",
+                                         "(1.45 MB read + 256 B written: tables and packed samples stay in L2)",
                          "other_kernels": other},
             "result": {"infidelity": infid, "acceptance": (eng.n_accepted.sum().item() /
                                                             (2.0 * eng.local_chains * sweeps * N * eng.steps_done))},

@@ -13,6 +13,8 @@
 // log cosh z is accumulated in product form: sum_j (|x_j| - ln 2) + log prod_j (1 + t_j e^{-2 i y_j}),
 // t_j = e^{-2|x_j|}, i.e. MUFU.EX2 + MUFU.SIN + MUFU.COS per hidden unit and one complex log per 8 units;
 // the phase is therefore defined mod 2 pi (as any sum of principal-branch logs is, after exp()).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace nkfb {
@@ -76,7 +78,7 @@ struct TcFwdArgs {
   int64_t n_groups;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGeom g = a.g;
   unsigned char *Bs = smem;                             // 3 splits of the current chunk
@@ -317,7 +319,13 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
   if (S < 2048) return 1;
   TcGeom g;
-  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden)) return 1;
+  // two CTAs per SM (each its own TMEM accumulator): one CTA's UMMAs and X-tile builds overlap the other's
+  // log-cosh epilogue; the W~ chunk of a CTA is sized for half of the shared memory
+  size_t budget = 104 * 1024;
+  if (const char *e = getenv("NKFB_TC_FWD_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
+  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, 0, budget) &&
+      !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden))
+    return 1;
   const size_t smem = g.b_chunk_bytes() + g.a_bytes() + (size_t)g.NN * 4 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
   if (smem > 227 * 1024) return 1;
 
@@ -361,7 +369,8 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
   a.n_groups = (tiles + TC_T - 1) / TC_T;
   NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count);
+  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+  const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);
   infid_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

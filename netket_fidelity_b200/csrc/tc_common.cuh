@@ -24,7 +24,8 @@ struct TcGeom {
 
 // cols: real columns to cover; extra_col_bytes: additional shared memory per column (pass B keeps the three
 // bf16 splits of a 128-sample Y tile); x_bytes: bytes of the X tile
-inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_bytes = 0, size_t x_bytes = 0) {
+inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_bytes = 0, size_t x_bytes = 0,
+                        size_t budget_bytes = 200 * 1024) {
   g->N = N;
   g->M = M;
   g->KT = ((N + 1 + 15) / 16) * 16;
@@ -32,7 +33,8 @@ inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_byte
   g->KS = g->KT / 16;
   if (x_bytes == 0) x_bytes = (size_t)g->KC * TC_ROWS * 16;
   // columns per chunk: multiple of 16, <= 256, and everything must fit in shared memory
-  const size_t budget = 200 * 1024 - x_bytes - 8192;
+  if (budget_bytes < x_bytes + 8192 + 4096) return false;
+  const size_t budget = budget_bytes - x_bytes - 8192;
   int nn_max = (int)std::min<size_t>(256, budget / ((size_t)3 * g->KC * 16 + extra_col_bytes));
   nn_max = (nn_max / 16) * 16;
   if (nn_max < 16) return false;

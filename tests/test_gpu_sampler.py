@@ -152,6 +152,56 @@ def test_fp32_samplers_agree_on_most_trajectories(h, algo):
     assert abs(na - nb) < 0.01 * na
 
 
+@pytest.fixture
+def kernel_path(monkeypatch):
+    """Selects which multiplicative kernel a 32-lane shape dispatches to: 'cta' (CTA-synchronous shared rows,
+    site_mode 0 only), 'pipe' (one chain per warp, pipelined) or 'generic' (lane-group kernel)."""
+    def set_(path):
+        monkeypatch.delenv("NKFB_RATIO_NOCTA", raising=False)
+        monkeypatch.delenv("NKFB_RATIO_NOPIPE", raising=False)
+        if path in ("pipe", "generic"):
+            monkeypatch.setenv("NKFB_RATIO_NOCTA", "1")
+        if path == "generic":
+            monkeypatch.setenv("NKFB_RATIO_NOPIPE", "1")
+    return set_
+
+
+@pytest.mark.parametrize("N,M", [(9, 300), (40, 130), (100, 400), (7, 500)])
+@pytest.mark.parametrize("path", ["cta", "pipe", "generic"])
+def test_fp64_multiplicative_kernels_agree_with_restatement(h, algo, kernel_path, N, M, path):
+    """The three forms of the multiplicative sampler (sampler_ratio.cuh) on 32-lane shapes, float64: each one
+    reproduces the trajectories of the float64 restatement (shared site sequence, chains continued from a
+    non-zero step offset so that chunk / RNG-batch phases are exercised)."""
+    algo(2)
+    kernel_path(path)
+    p = _net(N, M, 50 + N, 0.3 / np.sqrt(N))
+    n_chains, cl, nd = 5, 3, 1
+    ref, fin, nacc_ref = metropolis_local_b200(p, n_chains, cl, nd, N, seed=31337, site_mode=0, chain_offset=2,
+                                               step_offset=2 * N + 1)
+    got, state, nacc = _run(h, p, torch.complex128, n_chains, cl, nd, N, 31337, 0, chain_offset=2,
+                            step_offset=2 * N + 1)
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(state.cpu().numpy().view(np.uint32), fin)
+    assert nacc == nacc_ref
+
+
+@pytest.mark.parametrize("path", ["cta", "pipe", "generic"])
+def test_fp32_multiplicative_kernels_north_star_shape(h, algo, kernel_path, path):
+    """N = 100, M = 400 (the north-star shape), single precision, many more chains than one CTA holds: the three
+    kernels share random numbers, so all but a few per cent of the chains emit the samples of the additive kernel,
+    and the acceptance rates agree."""
+    N, M = 100, 400
+    p = _net(N, M, 11, 0.01)
+    algo(1)
+    a, _, na = _run(h, p, torch.complex64, 700, 4, 1, N, 5)
+    algo(2)
+    kernel_path(path)
+    b, _, nb = _run(h, p, torch.complex64, 700, 4, 1, N, 5)
+    same = np.all(a.reshape(700, -1) == b.reshape(700, -1), axis=1).mean()
+    assert same > 0.9, same
+    assert abs(na - nb) < 0.005 * na
+
+
 def _z_scores(counts, p, inflate):
     S = counts.sum()
     return (counts / S - p) / np.sqrt(p * (1 - p) * inflate / S)
