@@ -758,8 +758,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-template <typename R, int NP, int C, int GL, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, 1) sample_ratio_cta_kernel(NetDev<R> net, const R *ws, const R s0, const R s1,
+template <typename R, int NP, int C, int GL, int MAXW, int MINB>
+__global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDev<R> net, const R *ws, const R s0, const R s1,
                                                                    SampArgs a, const int *site_seq, const R *a0_seq,
                                                                    const int TSH) {
   using P = P2<R>;
@@ -1048,8 +1048,9 @@ __global__ void __launch_bounds__(32 * MAXW, 1) sample_ratio_cta_kernel(NetDev<R
   if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-// warps per CTA and log2 of the chunk length: `maxw` warps (one CTA per SM) for large launches; for small ones
-// (multi-GPU shards) enough CTAs to touch every SM, with shorter chunks so that several CTAs share an SM.
+// warps per CTA and log2 of the chunk length: `maxw` warps (one CTA per SM) for large launches -- a wave of CTAs
+// lasts (steps) x (latency of one step) almost independently of how many warps it holds, so fuller CTAs win over
+// a better-filled last wave (measured); small launches get enough CTAs to touch every SM and shorter chunks.
 inline void ratio_cta_shape(int64_t n_chains, int C, int sm_count, int maxw, int *W, int *TSH) {
   int64_t w = (n_chains + (int64_t)C * sm_count - 1) / ((int64_t)C * sm_count);
   if (w > maxw) w = maxw;
@@ -1062,18 +1063,18 @@ inline size_t ratio_cta_smem(int NP, int C, int W, int TSH) {
   return ((size_t)4 * (1 << TSH) * 4 * NP * 32 + (size_t)W * C * 128) * sizeof(R) + (size_t)W * C * PIPE_WR_ * 4;
 }
 
-template <typename R, int NP, int C, int GL, int MAXW = 16>
+template <typename R, int NP, int C, int GL, int MAXW = 16, int MINB = 1>
 static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
                             const int *site_seq, const R *a0_seq, cudaStream_t st) {
   int W, TSH;
   ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
   if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning override
   const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH);
-  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW>,
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   const int64_t blocks = (a.n_chains + (int64_t)C * W - 1) / ((int64_t)C * W);
-  sample_ratio_cta_kernel<R, NP, C, GL, MAXW><<<(unsigned)blocks, W * 32, smem, st>>>(
+  sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB><<<(unsigned)blocks, W * 32, smem, st>>>(
       make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a, site_seq, a0_seq, TSH);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

@@ -32,7 +32,10 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
   constexpr int GW = NP < 4 ? NP : 4;
 #if NKFB_L == 32
   if constexpr (NP <= 8) {
-    if (a.site_seq != nullptr && net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOCTA")) {
+    // small launches (a multi-GPU shard: fewer than ~40 chains per SM) are bound by the latency of one Metropolis
+    // step, not by throughput: there the one-chain-per-warp pipelined kernel below, which has the shorter step, wins
+    const bool big = a.n_chains >= (int64_t)40 * h->sm_count || getenv("NKFB_RATIO_NOPIPE") || getenv("NKFB_RATIO_FORCECTA");
+    if (a.site_seq != nullptr && big && net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOCTA")) {
       // shared site sequence: CTA-synchronous kernel, C chains per warp (z only: 4 NP words per chain)
       constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
       if (gl_one)
@@ -95,6 +98,10 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
       case 31: return launch_ratio_cta<NKFB_RT, 7, 2, 4>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 32: return launch_ratio_cta<NKFB_RT, 7, 4, 4>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 33: return launch_ratio_cta<NKFB_RT, 7, 3, 7>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 40: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 14, 2>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 41: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 10, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 42: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 16, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 43: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 8, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 34: return launch_ratio_cta<NKFB_RT, 7, 3, 4, 12>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 35: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 8>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 36: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 10>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);

@@ -159,6 +159,9 @@ def kernel_path(monkeypatch):
     def set_(path):
         monkeypatch.delenv("NKFB_RATIO_NOCTA", raising=False)
         monkeypatch.delenv("NKFB_RATIO_NOPIPE", raising=False)
+        monkeypatch.delenv("NKFB_RATIO_FORCECTA", raising=False)
+        if path == "cta":
+            monkeypatch.setenv("NKFB_RATIO_FORCECTA", "1")  # small launches default to the pipelined kernel
         if path in ("pipe", "generic"):
             monkeypatch.setenv("NKFB_RATIO_NOCTA", "1")
         if path == "generic":
