@@ -178,6 +178,14 @@ int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t
                          const void *log_val, const void *rho1, const double *sums,
                          double *grad_acc, void *stream);
 
+/* Weighted sum of log-derivatives over an arbitrary list of configurations (the building block of the exact,
+ * full-summation infidelity gradient: infidelity/overlap/exact.py:62-76, overlap_U/exact.py:71-88, where
+ * nkjax.vjp(conjugate=True) of |<psi|Phi>|^2 / <psi|psi> reduces to such a sum with complex weights):
+ *   acc_k += sum_s w_s conj O_k(x_s),   O_k = d log psi / d theta_k.
+ * packed: device (S, W32); weights: device (S) complex of net->dtype; acc: device double[2 P], flat layout. */
+int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *packed, int64_t S,
+                        const double local_states[2], const void *weights, double *acc, void *stream);
+
 /* I_grad = -acc / sums[4], cast to `dtype` (infidelity/overlap/expect.py:126-127).
  * grad_out: device (P) complex of `dtype`, flat layout. */
 int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums,

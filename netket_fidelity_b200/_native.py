@@ -22,7 +22,7 @@ SYMBOLS = [
     "nkfb_version", "nkfb_create", "nkfb_destroy", "nkfb_last_error", "nkfb_launch_count",
     "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample", "nkfb_sample_workspace_bytes",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
-    "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update", "nkfb_set_option",
+    "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update", "nkfb_set_option", "nkfb_weighted_score",
 ]
 
 OPT_SAMPLER_ALGO = 1
@@ -92,6 +92,7 @@ def load_library():
         lib.nkfb_renyi2.argtypes = [vp, P(RbmT), vp, i64, vp, P(dbl), vp, vp, vp, vp, vp]
         lib.nkfb_microbench.argtypes = [vp, i32, i32, P(dbl), vp]
         lib.nkfb_set_option.argtypes = [vp, i32, i64]
+        lib.nkfb_weighted_score.argtypes = [vp, P(RbmT), vp, i64, P(dbl), vp, vp, vp]
         lib.nkfb_optimizer_update.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, i64, i32, vp]
         for name in SYMBOLS:
             getattr(lib, name)  # AttributeError if the ABI drifted
@@ -337,6 +338,17 @@ class Handle:
                                                   _ptr(rho1), _ptr(sums), _ptr(grad_acc), _stream()),
                     "nkfb_infidelity_grad")
         return grad_acc
+
+    def weighted_score(self, net: RbmSpec, packed, local_states, weights, acc=None):
+        """acc_k += sum_s w_s conj O_k(x_s); weights (S,) complex of the net's dtype, acc (2P,) float64."""
+        S = packed.shape[0]
+        if acc is None:
+            acc = torch.zeros((2 * net.n_params,), dtype=torch.float64, device=packed.device)
+        ns = net.struct()
+        weights = weights.to(complex_dtype(net.code)).contiguous()
+        self._check(self.lib.nkfb_weighted_score(self.h, C.byref(ns), _ptr(packed), S, _ls(local_states),
+                                                 _ptr(weights), _ptr(acc), _stream()), "nkfb_weighted_score")
+        return acc
 
     def grad_finalize(self, grad_acc, sums, P, dtype):
         out = torch.empty((P,), dtype=dtype, device=grad_acc.device)

@@ -149,6 +149,7 @@ struct GradArgs {
   double *grad_acc;
   int n_splits;
   int64_t tiles_per_split;
+  const void *weights;  // nkfb_weighted_score: w_sig = weights[s], no eta term, log_val / rho1 / sums unused
 };
 
 template <typename R, int SPT>
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(NT) infid_grad_kernel(NetDev<R> psi, GradArgs 
   const R s0 = (R)a.s0, s1 = (R)a.s1, ssum = s0 + s1;
   const bool gate = (a.op2.kind == NKFB_OP_GATE);
   const int gidx = a.op2.idx;
-  const double F = a.sums[0] / a.sums[4];
+  const bool direct = a.weights != nullptr;
+  const double F = direct ? 0.0 : a.sums[0] / a.sums[4];
   const R cvc = a.has_cv ? (R)a.cv : R(0);
 
   load_w_chunk<R>(Ws, psi, chunk);
@@ -233,7 +235,9 @@ __global__ void __launch_bounds__(NT) infid_grad_kernel(NetDev<R> psi, GradArgs 
     for (int s = threadIdx.x; s < TS; s += NT) {
       const int64_t gs = s_base + s;
       cx<R> ws_ = mk<R>(0, 0), we_ = mk<R>(0, 0), rh_ = mk<R>(0, 0);
-      if (gs < a.S) {
+      if (gs < a.S && direct) {
+        ws_ = reinterpret_cast<const cx<R> *>(a.weights)[gs];
+      } else if (gs < a.S) {
         cx<R> l = reinterpret_cast<const cx<R> *>(a.log_val)[gs];
         cx<R> A = cexp(l);
         R A2 = abs2(A);
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(NT) infid_grad_kernel(NetDev<R> psi, GradArgs 
     }
     __syncthreads();
     rank1_tile<R, SPT>(G, Xs + row0 * XS, Ys, nrows);
+    if (direct) continue;  // uniform over the CTA
     __syncthreads();
     // ---------------- eta term: Y = w_eta * sum_c conj(rho_c) conj(tanh theta_psi(eta'_c))
     load_x_tile<R, SPT>(Xs, a.eta, s_base, a.S, N, s0, s1);
@@ -455,7 +460,8 @@ static int launch_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
 template <typename R, int SPT>
 static int launch_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
                        const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
-                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st) {
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st,
+                       const void *weights = nullptr) {
   constexpr int TS = TileCfg<SPT>::TS;
   GradArgs a;
   a.op2 = make_opdev(op2);
@@ -470,6 +476,7 @@ static int launch_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   a.rho1 = rho1;
   a.sums = sums;
   a.grad_acc = grad_acc;
+  a.weights = weights;
   const int N = psi->n_visible, M = psi->n_hidden;
   const int nchunks = (M + 1 + JC - 1) / JC;  // +1: pseudo-unit column for the visible bias
   const int rowblks = (N + 1 + 127) / 128;
@@ -586,6 +593,21 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
                                  st);
   return launch_grad<double, 4>(h, psi, op2, sigma, eta, S, local_states, cv_coeff, log_val, rho1, sums, grad_acc,
                                 st);
+}
+
+extern "C" int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *packed, int64_t S,
+                                   const double local_states[2], const void *weights, double *acc, void *stream) {
+  if (!h) return NKFB_ERR_INVALID;
+  int rc = check_net(h, net);
+  if (rc) return rc;
+  if (S <= 0) return NKFB_OK;
+  if (!packed || !weights || !acc) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->dtype == NKFB_F32)
+    return launch_grad<float, 8>(h, net, nullptr, packed, packed, S, local_states, NAN, nullptr, nullptr, nullptr, acc,
+                                 st, weights);
+  return launch_grad<double, 4>(h, net, nullptr, packed, packed, S, local_states, NAN, nullptr, nullptr, nullptr, acc,
+                                st, weights);
 }
 
 extern "C" int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums, int64_t P, int dtype,

@@ -11,7 +11,8 @@ from __future__ import annotations
 import torch
 
 from .. import _native as nv
-from ..nk.vqs import MCState
+from ..nk.stats import Stats
+from ..nk.vqs import MCState, FullSumState
 from .overlap.operator import InfidelityOperatorStandard
 from .overlap_U.operator import InfidelityOperatorUPsi
 
@@ -91,9 +92,58 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
     return I_stats, vstate._tree(flat)
 
 
+def infidelity_exact(vstate: FullSumState, op, return_grad: bool):
+    """Exact infidelity of two full-summation states and its gradient -- replaces
+    `infidelity_sampling_FullSumState` of infidelity/overlap/exact.py:53-78 (target |Phi> = target.to_array())
+    and infidelity/overlap_U/exact.py:62-90 (|Phi> = U target.to_array(normalize=False)):
+
+        F = |<psi|Phi>|^2 / (<psi|psi> <Phi|Phi>),      I = 1 - F,
+        nkjax.vjp(conjugate=True):  grad F_k = dF/dRe theta_k + i dF/dIm theta_k = 2 dF/d conj(theta_k)
+                                            = sum_x w_x conj O_k(x),
+        w_x = 2 [ conj(a) conj(psi_x) Phi_x / (n m) - F |psi_x|^2 / n ],  a = <psi|Phi>, n = <psi|psi>, m = <Phi|Phi>.
+
+    The 2^N amplitudes come from nkfb_logpsi (U Phi: the same kernel with the operator attached, which is what
+    `U.to_sparse() @ phi` computes), the sum over x from nkfb_weighted_score."""
+    if op.hilbert != vstate.hilbert:
+        raise TypeError("Hilbert spaces should match")
+    target = op.target
+    if not isinstance(target, FullSumState):
+        raise TypeError("Can only compute infidelity of exact states.")
+    if vstate._logstate is not None:
+        raise NotImplementedError("LogStateVector is supported as a target only")
+    dev = vstate.device
+    if isinstance(op, InfidelityOperatorStandard):
+        lt = target.log_amplitudes()
+    else:
+        if not hasattr(op._U, "_spec"):
+            raise TypeError("U must be an operator from netket_fidelity_b200.operator")
+        if target._logstate is not None or target._unitary is not None:
+            raise TypeError("InfidelityOperatorUPsi on exact states needs a plain RBM target")
+        lt = vstate._h.logpsi(target._spec(), target.all_states_packed(), target._ls,
+                              op._U._spec(dev)).to(torch.complex128)
+    lp = vstate.log_amplitudes()
+    psi = torch.exp(lp - lp.real.max())
+    T = torch.exp(lt - lt.real.max())
+    n = (psi.abs() ** 2).sum()
+    m = (T.abs() ** 2).sum()
+    a = (psi.conj() * T).sum()
+    F = (a.abs() ** 2 / (n * m)).real
+    I_stats = Stats(mean=float(1.0 - F.item()), error_of_mean=0.0, variance=0.0)
+    if not return_grad:
+        return I_stats
+    w = 2.0 * (a.conj() * psi.conj() * T / (n * m) - F * psi.abs() ** 2 / n)
+    acc = vstate._h.weighted_score(vstate._spec(), vstate.all_states_packed(), vstate._ls, w)
+    gF = torch.view_as_complex(acc.view(-1, 2).contiguous())
+    flat = (-gF).to(vstate._cdtype)
+    vstate._last_flat_grad = flat
+    return I_stats, vstate._tree(flat)
+
+
 def expect_dispatch(vstate, op, return_grad):
     from ..renyi2 import Renyi2EntanglementEntropy, renyi2_expect
     if isinstance(op, (InfidelityOperatorStandard, InfidelityOperatorUPsi)):
+        if isinstance(vstate, FullSumState):
+            return infidelity_exact(vstate, op, return_grad)
         return infidelity_expect(vstate, op, return_grad)
     if isinstance(op, Renyi2EntanglementEntropy):
         if return_grad:

@@ -27,6 +27,8 @@ class InfidelityOperatorStandard:
         if not isinstance(target, (MCState, FullSumState)):
             raise TypeError("The first argument should be a variational target.")
         cv_coeff = _check_cv(cv_coeff)
+        if isinstance(target, FullSumState):
+            cv_coeff = None  # overlap/operator.py:34-35: no control variate on exact states
         self._hilbert = target.hilbert
         self._target = target
         self._cv_coeff = cv_coeff

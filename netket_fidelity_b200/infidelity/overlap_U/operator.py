@@ -16,6 +16,8 @@ class InfidelityOperatorUPsi:
             raise ValueError("Only works with unitary gates. If the gate is non unitary "
                              "then you must sample from it. Use a different operator.")
         cv_coeff = _check_cv(cv_coeff)
+        if isinstance(state, FullSumState):
+            cv_coeff = None  # overlap_U/operator.py:40-41
         self._hilbert = state.hilbert
         self._target = state
         self._cv_coeff = cv_coeff

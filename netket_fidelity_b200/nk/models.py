@@ -43,3 +43,17 @@ class RBM:
 
     def __repr__(self):
         return f"RBM(alpha={self.alpha}, param_dtype={np.dtype(self.param_dtype)})"
+
+
+class LogStateVector:
+    """NetKet `nk.models.LogStateVector(hilbert)`: a state given by its 2^N log-amplitudes (parameter "logstate").
+    Used as a full-summation TARGET (examples/state_learning/state_learning.py:19-30)."""
+
+    def __init__(self, hilbert=None, param_dtype=complex):
+        self.hilbert = hilbert
+        self.param_dtype = param_dtype
+
+    is_complex = True
+
+    def __repr__(self):
+        return "LogStateVector()"

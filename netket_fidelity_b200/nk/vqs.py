@@ -35,7 +35,142 @@ def _world():
     return 1, 0
 
 
-class MCState:
+class _RBMStateBase:
+    """Parameter storage and amplitudes shared by MCState and FullSumState (flat complex device buffer)."""
+
+    def _init_params(self, hilbert, model, variables, seed, device):
+        if not torch.cuda.is_available():
+            raise nv.NkfbError("no CUDA device: netket_fidelity_b200 has no CPU fallback")
+        self._h = nv.get_handle(device)
+        self.device = self._h.device
+        self.hilbert = hilbert
+        self.model = model
+        N = hilbert.size
+        self._N = N
+        self._ls = tuple(hilbert.local_states)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(4), "little") + next(_seed_counter)
+        self._seed = int(seed)
+        self._unitary = None
+        if variables is not None:
+            params = variables["params"]
+            self._unitary = variables.get("unitary", None)
+            if model is None:
+                raise ValueError("`model` is needed to interpret `variables`")
+        else:
+            params = model.init(self._seed, N, self.device)
+        self._M = params["Dense"]["kernel"].shape[1]
+        self._W32 = (N + 31) // 32
+        self._alloc_flat(params)
+
+    def _params_changed(self):
+        pass
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_flat(self, params):
+        N, M = self._N, self._M
+        cdt = {torch.float64: torch.complex128, torch.float32: torch.complex64,
+               torch.complex128: torch.complex128, torch.complex64: torch.complex64}[params["Dense"]["kernel"].dtype]
+        self._cdtype = cdt
+        self._flat = torch.zeros((M + N * M + N,), dtype=cdt, device=self.device)
+        self._has_bias = "bias" in params["Dense"]
+        self._has_vbias = "visible_bias" in params
+        self._set_params(params)
+
+    def _views(self):
+        N, M = self._N, self._M
+        b = self._flat[:M]
+        k = self._flat[M:M + N * M].view(N, M)
+        a = self._flat[M + N * M:]
+        return k, b, a
+
+    def _set_params(self, params):
+        k, b, a = self._views()
+        k.copy_(torch.as_tensor(params["Dense"]["kernel"]).to(self.device))
+        if self._has_bias:
+            b.copy_(torch.as_tensor(params["Dense"]["bias"]).to(self.device))
+        if self._has_vbias:
+            a.copy_(torch.as_tensor(params["visible_bias"]).to(self.device))
+        self._params_changed()
+
+    def _spec(self) -> nv.RbmSpec:
+        k, b, a = self._views()
+        return nv.RbmSpec(k, b if self._has_bias else None, a if self._has_vbias else None)
+
+    def _tree(self, flat):
+        """(P,) complex flat vector -> parameter-shaped dict (real part for real-parameter models)."""
+        N, M = self._N, self._M
+        real = not self.model.is_complex
+        f = (lambda t: t.real) if real else (lambda t: t)
+        out = {"Dense": {"kernel": f(flat[M:M + N * M].view(N, M))}}
+        if self._has_bias:
+            out["Dense"]["bias"] = f(flat[:M])
+        if self._has_vbias:
+            out["visible_bias"] = f(flat[M + N * M:])
+        return out
+
+    def _flatten_tree(self, tree):
+        """parameter-shaped dict -> (P,) complex flat device vector (inverse of `_tree`)."""
+        N, M = self._N, self._M
+        flat = torch.zeros_like(self._flat)
+        flat[M:M + N * M].view(N, M).copy_(torch.as_tensor(tree["Dense"]["kernel"]).to(self.device))
+        if self._has_bias:
+            flat[:M].copy_(torch.as_tensor(tree["Dense"]["bias"]).to(self.device))
+        if self._has_vbias:
+            flat[M + N * M:].copy_(torch.as_tensor(tree["visible_bias"]).to(self.device))
+        return flat
+
+    @property
+    def parameters(self):
+        return self._tree(self._flat)
+
+    @parameters.setter
+    def parameters(self, params):
+        self._set_params(params)
+
+    @property
+    def model_state(self):
+        return {} if self._unitary is None else {"unitary": self._unitary}
+
+    @property
+    def variables(self):
+        return {"params": self.parameters, **self.model_state}
+
+    @variables.setter
+    def variables(self, v):
+        self._unitary = v.get("unitary", None)
+        self._set_params(v["params"])
+
+    @property
+    def n_parameters(self):
+        n = self._N * self._M
+        return n + (self._M if self._has_bias else 0) + (self._N if self._has_vbias else 0)
+
+    def _op_spec(self):
+        return None if self._unitary is None else self._unitary._spec(self.device)
+
+    # ------------------------------------------------------------------ amplitudes
+    def log_value(self, x):
+        """log psi(x) (or log (U phi)(x) when a unitary is attached).  x: (..., N) tensor/array of local states."""
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.device)
+        shape = x.shape[:-1]
+        xf = x.reshape(-1, self._N).to(torch.float64).contiguous()
+        p = self._h.pack(xf, self._ls)
+        return self._h.logpsi(self._spec(), p, self._ls, self._op_spec()).view(shape)
+
+    def to_array(self, normalize=True):
+        if self._N > 24:
+            raise ValueError("to_array: Hilbert space too large")
+        st = torch.tensor(self.hilbert.all_states(), dtype=torch.float64, device=self.device)
+        lv = self.log_value(st).to(torch.complex128)
+        lv = lv - lv.real.max()
+        psi = torch.exp(lv)
+        if normalize:
+            psi = psi / torch.linalg.vector_norm(psi)
+        return psi
+
+
+class MCState(_RBMStateBase):
     def __init__(self, sampler, model=None, *, n_samples=None, n_samples_per_rank=None, n_discard_per_chain=None,
                  chunk_size=None, variables=None, seed=None, sampler_seed=None, device=None, apply_fun=None):
         if chunk_size is not None:
@@ -93,88 +228,8 @@ class MCState:
         self._n_steps_total = 0
         self._ws = None
 
-    # ------------------------------------------------------------------ parameters
-    def _alloc_flat(self, params):
-        N, M = self._N, self._M
-        cdt = {torch.float64: torch.complex128, torch.float32: torch.complex64,
-               torch.complex128: torch.complex128, torch.complex64: torch.complex64}[params["Dense"]["kernel"].dtype]
-        self._cdtype = cdt
-        self._flat = torch.zeros((M + N * M + N,), dtype=cdt, device=self.device)
-        self._has_bias = "bias" in params["Dense"]
-        self._has_vbias = "visible_bias" in params
-        self._set_params(params)
-
-    def _views(self):
-        N, M = self._N, self._M
-        b = self._flat[:M]
-        k = self._flat[M:M + N * M].view(N, M)
-        a = self._flat[M + N * M:]
-        return k, b, a
-
-    def _set_params(self, params):
-        k, b, a = self._views()
-        k.copy_(torch.as_tensor(params["Dense"]["kernel"]).to(self.device))
-        if self._has_bias:
-            b.copy_(torch.as_tensor(params["Dense"]["bias"]).to(self.device))
-        if self._has_vbias:
-            a.copy_(torch.as_tensor(params["visible_bias"]).to(self.device))
-        self._params_changed()
-
     def _params_changed(self):
         self._samples_packed = None
-
-    def _spec(self) -> nv.RbmSpec:
-        k, b, a = self._views()
-        return nv.RbmSpec(k, b if self._has_bias else None, a if self._has_vbias else None)
-
-    def _tree(self, flat):
-        """(P,) complex flat vector -> parameter-shaped dict (real part for real-parameter models)."""
-        N, M = self._N, self._M
-        real = not self.model.is_complex
-        f = (lambda t: t.real) if real else (lambda t: t)
-        out = {"Dense": {"kernel": f(flat[M:M + N * M].view(N, M))}}
-        if self._has_bias:
-            out["Dense"]["bias"] = f(flat[:M])
-        if self._has_vbias:
-            out["visible_bias"] = f(flat[M + N * M:])
-        return out
-
-    def _flatten_tree(self, tree):
-        """parameter-shaped dict -> (P,) complex flat device vector (inverse of `_tree`)."""
-        N, M = self._N, self._M
-        flat = torch.zeros_like(self._flat)
-        flat[M:M + N * M].view(N, M).copy_(torch.as_tensor(tree["Dense"]["kernel"]).to(self.device))
-        if self._has_bias:
-            flat[:M].copy_(torch.as_tensor(tree["Dense"]["bias"]).to(self.device))
-        if self._has_vbias:
-            flat[M + N * M:].copy_(torch.as_tensor(tree["visible_bias"]).to(self.device))
-        return flat
-
-    @property
-    def parameters(self):
-        return self._tree(self._flat)
-
-    @parameters.setter
-    def parameters(self, params):
-        self._set_params(params)
-
-    @property
-    def model_state(self):
-        return {} if self._unitary is None else {"unitary": self._unitary}
-
-    @property
-    def variables(self):
-        return {"params": self.parameters, **self.model_state}
-
-    @variables.setter
-    def variables(self, v):
-        self._unitary = v.get("unitary", None)
-        self._set_params(v["params"])
-
-    @property
-    def n_parameters(self):
-        n = self._N * self._M
-        return n + (self._M if self._has_bias else 0) + (self._N if self._has_vbias else 0)
 
     # ------------------------------------------------------------------ sampling
     @property
@@ -188,9 +243,6 @@ class MCState:
     @property
     def chain_length(self):
         return self._chain_length
-
-    def _op_spec(self):
-        return None if self._unitary is None else self._unitary._spec(self.device)
 
     def reset(self):
         """Drop the sample cache; chain positions are kept (NetKet `MCState.reset`)."""
@@ -230,26 +282,6 @@ class MCState:
     def acceptance(self):
         return float(self._n_accepted.item()) / max(1, self._n_steps_total)
 
-    # ------------------------------------------------------------------ amplitudes
-    def log_value(self, x):
-        """log psi(x) (or log (U phi)(x) when a unitary is attached).  x: (..., N) tensor/array of local states."""
-        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(self.device)
-        shape = x.shape[:-1]
-        xf = x.reshape(-1, self._N).to(torch.float64).contiguous()
-        p = self._h.pack(xf, self._ls)
-        return self._h.logpsi(self._spec(), p, self._ls, self._op_spec()).view(shape)
-
-    def to_array(self, normalize=True):
-        if self._N > 24:
-            raise ValueError("to_array: Hilbert space too large")
-        st = torch.tensor(self.hilbert.all_states(), dtype=torch.float64, device=self.device)
-        lv = self.log_value(st).to(torch.complex128)
-        lv = lv - lv.real.max()
-        psi = torch.exp(lv)
-        if normalize:
-            psi = psi / torch.linalg.vector_norm(psi)
-        return psi
-
     # ------------------------------------------------------------------ expectation values
     def expect(self, op):
         from ..infidelity.expect import expect_dispatch
@@ -285,12 +317,90 @@ class MCState:
                 f"n_parameters={self.n_parameters})")
 
 
-class FullSumState:
-    """Exact (full-summation) states are OUT OF SCOPE of the GPU hot path.
-    The class exists so that `isinstance(..., FullSumState)` checks of the reference's factory
-    (infidelity/logic.py:154-161) keep their meaning; constructing one raises."""
+class FullSumState(_RBMStateBase):
+    """Exact (full-summation) variational state, NetKet `nk.vqs.FullSumState(hilbert, model)`, for N <= 24.
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError(
-            "FullSumState (exact summation over 2^N states) is not part of the B200 hot path; "
-            "use MCState, or the CPU oracle in oracle/exact.py for N <= 12 ground truth")
+    The amplitudes of all 2^N configurations come from the batched log-amplitude kernel (nkfb_logpsi); the exact
+    infidelity and its gradient (reference: infidelity/overlap/exact.py:53-78, overlap_U/exact.py:62-90) are a
+    handful of reductions over that vector plus ONE weighted sum of log-derivatives (nkfb_weighted_score).
+    Models: the RBM (variational or target) and `LogStateVector` (a target given by its 2^N log-amplitudes,
+    examples/state_learning/state_learning.py:19-30)."""
+
+    def __init__(self, hilbert, model=None, *, variables=None, seed=None, chunk_size=None, device=None):
+        from .models import LogStateVector
+        if hilbert.size > 24:
+            raise ValueError("FullSumState: Hilbert space too large to enumerate (N > 24)")
+        self._logstate = None
+        if isinstance(model, LogStateVector):
+            if not torch.cuda.is_available():
+                raise nv.NkfbError("no CUDA device: netket_fidelity_b200 has no CPU fallback")
+            self._h = nv.get_handle(device)
+            self.device = self._h.device
+            self.hilbert, self.model = hilbert, model
+            self._N, self._ls = hilbert.size, tuple(hilbert.local_states)
+            self._W32 = (self._N + 31) // 32
+            self._unitary = None
+            init = variables["params"]["logstate"] if variables is not None else torch.zeros(2 ** self._N)
+            self._logstate = torch.as_tensor(init).to(torch.complex128).to(self.device).clone()
+        else:
+            self._init_params(hilbert, model, variables, seed, device)
+        self._all_packed = None
+
+    # LogStateVector targets carry their own parameter tree
+    @property
+    def parameters(self):
+        if self._logstate is not None:
+            return {"logstate": self._logstate}
+        return self._tree(self._flat)
+
+    @parameters.setter
+    def parameters(self, params):
+        if self._logstate is not None:
+            self._logstate = torch.as_tensor(params["logstate"]).to(torch.complex128).to(self.device).clone()
+        else:
+            self._set_params(params)
+
+    @property
+    def n_parameters(self):
+        if self._logstate is not None:
+            return self._logstate.numel()
+        return _RBMStateBase.n_parameters.fget(self)
+
+    @property
+    def n_samples(self):
+        return 2 ** self._N
+
+    def reset(self):
+        pass
+
+    def all_states_packed(self):
+        """(2^N, W32) int32: every configuration, in `hilbert.all_states()` order."""
+        if self._all_packed is None:
+            st = torch.tensor(self.hilbert.all_states(), dtype=torch.float64, device=self.device)
+            self._all_packed = self._h.pack(st.contiguous(), self._ls)
+        return self._all_packed
+
+    def log_amplitudes(self):
+        """log psi(x) (log (U phi)(x) with a unitary attached) for all configurations, complex128."""
+        if self._logstate is not None:
+            return self._logstate
+        lv = self._h.logpsi(self._spec(), self.all_states_packed(), self._ls, self._op_spec())
+        return lv.to(torch.complex128)
+
+    def to_array(self, normalize=True):
+        lv = self.log_amplitudes()
+        psi = torch.exp(lv - lv.real.max()) if normalize else torch.exp(lv)
+        if normalize:
+            psi = psi / torch.linalg.vector_norm(psi)
+        return psi
+
+    def expect(self, op):
+        from ..infidelity.expect import expect_dispatch
+        return expect_dispatch(self, op, return_grad=False)
+
+    def expect_and_grad(self, op, *, mutable=None):
+        from ..infidelity.expect import expect_dispatch
+        return expect_dispatch(self, op, return_grad=True)
+
+    def __repr__(self):
+        return f"FullSumState(hilbert={self.hilbert}, n_parameters={self.n_parameters})"

@@ -192,3 +192,76 @@ def test_log_value_to_array_and_sample_Upsi_state():
     ref = logpsi_U(_to_oracle(vs), oops.Rx(5, 2, 0.7), st)
     got = tgt.log_value(st).cpu().numpy()
     np.testing.assert_allclose(np.exp(got - ref), 1.0, rtol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------- FullSumState
+@pytest.mark.parametrize("which", ["Identity", "Rx", "Ry", "Hadamard"])
+@pytest.mark.parametrize("pdtype", [float, complex])
+@pytest.mark.parametrize("N,alpha", [(3, 1), (6, 2)])
+def test_FullSumState_like_the_reference_test(which, pdtype, N, alpha):
+    """test/test_infidelity_operator.py:140-182: the exact (full-summation) path.  expect == expect_and_grad,
+    mean == exact infidelity, gradient == central differences of the exact infidelity (the reference accepts
+    rel 0.5; the closed form here agrees to 1e-6), cv_coeff silently dropped (overlap/operator.py:34-35)."""
+    hi = nk.hilbert.Spin(0.5, N)
+    ma = nk.models.RBM(alpha=alpha, param_dtype=pdtype, stddev=0.3)
+    vs_t = nk.vqs.FullSumState(hi, ma, seed=11)
+    vs = nk.vqs.FullSumState(hi, ma, seed=22)
+    U, oU = {"Identity": (None, None), "Rx": (nkf.operator.Rx(hi, 1, 0.4), oops.Rx(N, 1, 0.4)),
+             "Ry": (nkf.operator.Ry(hi, 0, 0.7), oops.Ry(N, 0, 0.7)),
+             "Hadamard": (nkf.operator.Hadamard(hi, 2), oops.Hadamard(N, 2))}[which]
+    psi, phi = _to_oracle(vs), _to_oracle(vs_t)
+    I_exact = infidelity_exact(psi, phi, oU)
+    g_exact = infidelity_exact_grad_fd(psi, phi, oU, 1e-5)
+    I_op = nkf.InfidelityOperator(vs_t, U=U, U_dagger=None if U is None else U.H, cv_coeff=-0.5, is_unitary=True)
+    assert I_op.cv_coeff is None
+    I_stat1 = vs.expect(I_op)
+    I_stat, I_grad = vs.expect_and_grad(I_op)
+    assert I_stat1.error_of_mean == 0.0 and I_stat1.variance == 0.0
+    assert I_stat1.mean == pytest.approx(I_exact, abs=1e-10)
+    assert I_stat1.mean == pytest.approx(I_stat.mean, abs=1e-12)
+    g = _flat(I_grad)
+    if pdtype is float:
+        g_exact = g_exact.real
+        assert not np.iscomplexobj(g)
+    np.testing.assert_allclose(g, g_exact, atol=2e-7 * max(1.0, np.abs(g_exact).max()))
+
+
+def test_FullSumState_errors_and_to_array():
+    hi = nk.hilbert.Spin(0.5, 4)
+    ma = nk.models.RBM(alpha=1, param_dtype=complex)
+    vs = nk.vqs.FullSumState(hi, ma, seed=3)
+    arr = vs.to_array()
+    assert arr.shape == (16,) and abs(float((arr.abs() ** 2).sum()) - 1.0) < 1e-12
+    np.testing.assert_allclose(arr.cpu().numpy(), oops_to_array(_to_oracle(vs)), atol=1e-12)
+    sa = nk.sampler.MetropolisLocal(hilbert=hi, n_chains_per_rank=16)
+    mc = nk.vqs.MCState(sampler=sa, model=ma, n_samples=64, seed=1)
+    with pytest.raises(TypeError, match="exact states"):
+        vs.expect(nkf.InfidelityOperator(mc))
+    with pytest.raises(TypeError):
+        vs.expect(nkf.InfidelityOperator(nk.vqs.FullSumState(nk.hilbert.Spin(0.5, 3), ma, seed=1)))
+
+
+def oops_to_array(p):
+    from oracle.exact import to_array
+    return to_array(p)
+
+
+def test_state_learning_example_flow():
+    """examples/state_learning/state_learning.py: a LogStateVector target (here the exact ground state of a 2x2
+    transverse-field Ising model), an RBM FullSumState trained with InfidelityOptimizer + Adam."""
+    g = nk.graph.Hypercube(2, 2) if hasattr(nk.graph, "Hypercube") else nk.graph.Chain(4)
+    hi = nk.hilbert.Spin(0.5, 4)
+    H = oops.Ising(4, oops.chain_edges(4), 1.0, 1.0).to_dense().real
+    w, v = np.linalg.eigh(H)
+    psi0 = v[:, 0]
+    vs_target = nk.vqs.FullSumState(hi, nk.models.LogStateVector(hi))
+    vs_target.parameters = {"logstate": torch.tensor(np.log(psi0 + 0j))}
+    np.testing.assert_allclose(np.abs(vs_target.to_array().cpu().numpy()), np.abs(psi0), atol=1e-12)
+    vs = nk.vqs.FullSumState(hi, nk.models.RBM(alpha=2, param_dtype=complex, stddev=0.05), seed=5)
+    inf = nkf.InfidelityOperator(vs_target)
+    I0 = vs.expect(inf).mean
+    driver = nkf.driver.InfidelityOptimizer(vs_target, nk.optimizer.Adam(learning_rate=0.02), variational_state=vs)
+    log = nk.logging.RuntimeLog()
+    driver.run(300, out=log, show_progress=False)
+    I1 = vs.expect(inf).mean
+    assert I1 < 0.02 < I0, (I0, I1)
