@@ -139,12 +139,41 @@ def infidelity_exact(vstate: FullSumState, op, return_grad: bool):
     return I_stats, vstate._tree(flat)
 
 
+def diagonal_expect(vstate, op):
+    """<c0 + sum_i c_i sigma^z_i>: sample mean over the packed samples (MCState) or the exact average over
+    |psi|^2 (FullSumState).  sigma^z_i = (2 x_i - s0 - s1) / (s1 - s0) in terms of the local-state value x_i."""
+    if op.hilbert != vstate.hilbert:
+        raise TypeError("Hilbert spaces should match")
+    dev = vstate.device
+    s0, s1 = vstate._ls
+    c = torch.tensor(op.coeffs, dtype=torch.float64, device=dev)
+    if isinstance(vstate, FullSumState):
+        x = torch.tensor(vstate.hilbert.all_states(), dtype=torch.float64, device=dev)
+        vals = op.const + ((2.0 * x - s0 - s1) / (s1 - s0)) @ c
+        p = vstate.to_array().abs() ** 2
+        mean = float((p * vals).sum().item())
+        var = float((p * (vals - mean) ** 2).sum().item())
+        return Stats(mean=mean, error_of_mean=0.0, variance=var)
+    pk = vstate.samples_packed()
+    x = vstate._h.unpack(pk.view(-1, pk.shape[-1]), vstate._N, vstate._ls, torch.float64)
+    vals = op.const + ((2.0 * x - s0 - s1) / (s1 - s0)) @ c
+    sums = torch.zeros(8, dtype=torch.float64, device=dev)
+    sums[0], sums[1], sums[4] = vals.sum(), (vals * vals).sum(), float(vals.numel())
+    _allreduce(sums)
+    return vstate._stats_of(vals.contiguous(), pk.shape[0], sums=sums)
+
+
 def expect_dispatch(vstate, op, return_grad):
     from ..renyi2 import Renyi2EntanglementEntropy, renyi2_expect
     if isinstance(op, (InfidelityOperatorStandard, InfidelityOperatorUPsi)):
         if isinstance(vstate, FullSumState):
             return infidelity_exact(vstate, op, return_grad)
         return infidelity_expect(vstate, op, return_grad)
+    from ..nk.operator.spin import DiagonalZ
+    if isinstance(op, DiagonalZ):
+        if return_grad:
+            raise NotImplementedError("gradient of a diagonal observable")
+        return diagonal_expect(vstate, op)
     if isinstance(op, Renyi2EntanglementEntropy):
         if return_grad:
             raise NotImplementedError("gradient of the Renyi-2 entropy")

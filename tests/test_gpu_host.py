@@ -265,3 +265,27 @@ def test_state_learning_example_flow():
     driver.run(300, out=log, show_progress=False)
     I1 = vs.expect(inf).mean
     assert I1 < 0.02 < I0, (I0, I1)
+
+
+def test_examples_run_short():
+    """The ported reference examples (examples/): a short adiabatic sweep (Trotter sequencing: Z half-steps on the
+    visible bias + one Rx optimisation per site, reference examples/adiabatic_sweeping) and state learning on a
+    3x3 lattice (reference examples/state_learning)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "examples", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    ts, obs, infid = load("adiabatic_sweeping").main(["--tf", "0.1", "--n-iter", "40", "--n-samples", "4096",
+                                                      "--n-chains", "256", "--quiet"])
+    assert len(obs) == 2 and all(abs(o.mean) < 0.2 for o in obs)      # starts in |+>^N: <sigma^z> ~ 0
+    assert all(i < 5e-3 for i in infid), infid                         # each small rotation is tracked closely
+    log = load("state_learning").main(["--length", "3", "--n-iter", "150"])
+    I = np.asarray(log.data["Infidelity"]["Mean"] if isinstance(log.data["Infidelity"], dict) else
+                   [v for v in log.data["Infidelity"]])
+    assert I.ravel()[-1] < 0.5 * I.ravel()[0]
