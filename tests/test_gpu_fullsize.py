@@ -1,0 +1,154 @@
+"""The BASELINE.json configurations at their FULL sizes (C2 2^16, C3 2^18, C4 2^20 sample pairs,
+C5 2^20 samples), checked through size-independent properties of the estimators -- the oracle finishes only a
+few hundred samples of these shapes in seconds, so at full size the CUDA path is held to invariants that need no
+reference values:
+
+  * E_chi |A|^2 = 1 for a unitary U (the control variate has zero mean), so  mean|A|^2  sits within 5 sigma of 1;
+  * the control-variates correction leaves the estimate unchanged and does not increase its variance;
+  * psi = phi, U = 1:  L_s = 1 for every sample, infidelity exactly 0, gradient 0;
+  * the whole step is independent of how the chains are sharded (two half shards == the full run: samples
+    bit-identical, sums equal to fp64 rounding, gradient to the fp32 rounding of the per-shard partial sums);
+  * the tensor-core kernels agree with the CUDA-core kernels on the same 2^20 samples;
+  * Renyi-2: S2(A) = S2(complement of A) for a pure state, S2 = 0 for a product state.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from netket_fidelity_b200 import _native as nv
+from netket_fidelity_b200.engine import InfidelityStep, StepConfig
+from netket_fidelity_b200.workloads import make_workload, device_ops, random_rbm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _specs(w, seeds=(1234, 5678), std=0.01):
+    return [nv.RbmSpec(*[t.to(DEV) if t is not None else None
+                         for t in random_rbm(w["N"], w["M"], s, torch.complex64, w["vb"], std=std)]) for s in seeds]
+
+
+def _engine(w, n_chains=None, cv=-0.5, seed=77):
+    U, Ud = device_ops(w, torch.device(DEV))
+    cfg = StepConfig(n_chains or w["n_chains"], w["chain_length"], 5, w["N"], seed=seed, cv_coeff=cv)
+    return InfidelityStep(w["N"], w["M"], cfg, w["mode"], U, Ud, device=torch.device(DEV))
+
+
+@pytest.mark.parametrize("name", ["C2", "C4"])
+def test_unitary_configs_full_size_invariants(name):
+    w = make_workload(name)
+    psi, phi = _specs(w)
+    eng = _engine(w)
+    sums, L, grad = eng.step(psi, phi)
+    s = sums.cpu().numpy()
+    n = s[4]
+    assert n == w["n_chains"] * w["chain_length"]
+    A2 = eng.last["log_val"].real.double().mul(2).exp()
+    m, sd = A2.mean().item(), A2.std().item()
+    # E|A|^2 = 1; chains are correlated, so allow the error of the mean a factor sqrt(8)
+    assert abs(m - 1.0) < 5 * sd * math.sqrt(8.0 / n) + 1e-6, (m, sd)
+    F_cv, var_cv = s[0] / n, s[1] / n - (s[0] / n) ** 2
+    # same samples without the control variate
+    eng.cfg.cv_coeff = None
+    sums0, L0, _ = eng.estimate(psi, phi, return_grad=False)
+    s0 = sums0.cpu().numpy()
+    F_0, var_0 = s0[0] / n, s0[1] / n - (s0[0] / n) ** 2
+    assert abs(F_cv - F_0) < 5 * math.sqrt(8.0 * max(var_0, 1e-12) / n) + 1e-7
+    assert var_cv <= var_0 * 1.0001
+    assert torch.isfinite(torch.view_as_real(grad)).all()
+    acc = eng.n_accepted.sum().item() / (2.0 * w["n_chains"] * (5 + w["chain_length"]) * w["N"])
+    assert 0.5 < acc <= 1.0
+
+
+def test_identical_states_give_zero_infidelity_at_full_size():
+    w = dict(make_workload("C4"), mode="standard")
+    psi, _ = _specs(w)
+    eng = _engine(w)
+    sums, L, grad = eng.step(psi, psi)
+    assert torch.all(L == 1.0)
+    s = sums.cpu().numpy()
+    assert s[0] / s[4] == 1.0
+    assert torch.view_as_real(grad).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
+def test_step_is_independent_of_the_sharding_at_full_size(name):
+    """Rank r of G owns chains [r n / G, (r+1) n / G): the union of two half-shard steps is the full step."""
+    w = make_workload(name)
+    psi, phi = _specs(w)
+    full = _engine(w)
+    sums, L, grad = full.step(psi, phi)
+    half = w["n_chains"] // 2
+    parts = []
+    for r in range(2):
+        e = _engine(w)
+        e.chain_offset, e.local_chains = r * half, half          # what parallel.shard_chains returns for rank r of 2
+        e.state_psi, e.state_phi = e.state_psi[:half].clone(), e.state_phi[:half].clone()
+        e.sigma, e.eta = e.sigma[:half].clone(), e.eta[:half].clone()
+        e.S_local = half * w["chain_length"]
+        e.sample(psi, phi)
+        parts.append(e)
+    sig = torch.cat([p.sigma for p in parts])
+    eta = torch.cat([p.eta for p in parts])
+    assert torch.equal(sig, full.sigma) and torch.equal(eta, full.eta)
+    # estimator + gradient of the two shards, reduced as the all-reduces would
+    acc = torch.zeros_like(full.acc)
+    h = full.h
+    W32 = full.W32
+    ls, cv = full.cfg.local_states, full.cfg.cv_coeff
+    fw = [h.infidelity_fwd(psi, phi, p.sigma.view(-1, W32), p.eta.view(-1, W32), ls, cv, full.op1, full.op2,
+                           full.op4, sums=acc[:8]) for p in parts]
+    np.testing.assert_allclose(acc[:8].cpu().numpy(), sums.cpu().numpy(), rtol=1e-12)
+    for p, (lv, Lp, rho1, _) in zip(parts, fw):
+        h.infidelity_grad(psi, p.sigma.view(-1, W32), p.eta.view(-1, W32), ls, cv, lv, rho1, acc[:8], op2=full.op2,
+                          grad_acc=acc[8:])
+    g2 = h.grad_finalize(acc[8:], acc[:8], full.P, torch.complex64)
+    scale = torch.view_as_real(grad).abs().max().item()
+    # the kernels accumulate fp32 partial sums over their own range of sample tiles (tens of thousands of O(1)
+    # terms that cancel to an O(0.05) mean) before the fp64 atomics, and a shard changes the ranges: agreement to
+    # that rounding, a few 1e-4 of the largest entry -- an order of magnitude below the Monte-Carlo error
+    assert (torch.view_as_real(g2 - grad).abs().max().item()) <= 5e-4 * scale + 1e-9
+
+
+def test_tensor_core_and_cuda_core_kernels_agree_at_full_size(monkeypatch):
+    w = make_workload("C4")
+    psi, phi = _specs(w)
+    eng = _engine(w)
+    sums, L, grad = eng.step(psi, phi)
+    sums, L, grad = sums.clone(), L.clone(), grad.clone()
+    monkeypatch.setenv("NKFB_FWD_IMPL", "simt")
+    monkeypatch.setenv("NKFB_GRAD_IMPL", "simt")
+    sums2, L2, grad2 = eng.estimate(psi, phi)
+    np.testing.assert_allclose(sums2.cpu().numpy()[:5], sums.cpu().numpy()[:5], rtol=2e-6)
+    # per-sample estimator: measured mean |dL| 3e-6, worst of 2^20 samples 5e-5 relative (|A|^2 = 35 there);
+    # the log-amplitude combination l itself agrees to 5e-5 absolute at worst, 9e-6 on average
+    dL = (L2 - L).abs() / (1.0 + L.abs())
+    assert dL.max().item() < 2e-4 and dL.mean().item() < 1e-5
+    scale = torch.view_as_real(grad).abs().max().item()
+    assert torch.view_as_real(grad2 - grad).abs().max().item() < 5e-4 * scale   # fp32 partial sums, see above
+
+
+def test_renyi2_full_size_symmetry_and_product_state():
+    """C5: 8x8 lattice (N = 64), RBM alpha = 2, 2^20 samples, subsystem = half of the system."""
+    import netket_fidelity_b200 as nkf
+    from netket_fidelity_b200 import nk
+    N = 64
+    hi = nk.hilbert.Spin(0.5, N)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains_per_rank=16384)
+    vs = nk.vqs.MCState(sa, nk.models.RBM(alpha=2, param_dtype="complex64", stddev=0.05), n_samples=2 ** 20,
+                        n_discard_per_chain=10, seed=9)
+    A, B = list(range(32)), list(range(32, 64))
+    sA = vs.expect(nkf.renyi2.Renyi2EntanglementEntropy(hi, A))
+    sB = vs.expect(nkf.renyi2.Renyi2EntanglementEntropy(hi, B))
+    assert vs.n_samples == 2 ** 20
+    assert sA.mean > -5 * sA.error_of_mean
+    assert abs(sA.mean - sB.mean) < 5 * math.hypot(sA.error_of_mean, sB.error_of_mean) + 1e-6, (sA, sB)
+    # product state: kernel = 0 -> psi(x) = prod_i exp(a_i x_i) (times a constant): S2 = 0 for any partition
+    p = vs.parameters
+    p["Dense"]["kernel"] = torch.zeros_like(p["Dense"]["kernel"])
+    vs.parameters = p
+    vs.reset()
+    s0 = vs.expect(nkf.renyi2.Renyi2EntanglementEntropy(hi, A))
+    assert abs(s0.mean) < 1e-5, s0
