@@ -297,7 +297,7 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
   a.xbound = reinterpret_cast<const float *>((const char *)ws + b_off * rsz);
   // shared site sequence on full warps: table of the proposal sites of this call for the CTA-synchronous kernel
   const uint64_t n_steps = (uint64_t)(a.n_discard + a.chain_length) * (uint64_t)a.sweep_size;
-  if (a.site_mode == 0 && L == 32 && NP <= 8 && N <= 32 * PIPE_WR && n_steps > 0 && n_steps <= (uint64_t)SITE_SEQ_CAP) {
+  if (a.site_mode == 0 && L == 32 && NP <= 8 && n_steps > 0 && n_steps <= (uint64_t)SITE_SEQ_CAP) {
     char *seq = (char *)ws + seq_ws_offset_reals(N, M) * rsz;
     int *site_seq = reinterpret_cast<int *>(seq);
     void *a0_seq = seq + (size_t)SITE_SEQ_CAP * 4;

@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
   using P = P2<R>;
   using V = typename P::V;
   using D = WarpDecide<R>;
-  constexpr int L = 32, SB = 128, WR = PIPE_WR_;
+  constexpr int L = 32, SB = 128;
   constexpr int NG = (NP + GL - 1) / GL;
   constexpr int ROW = 4 * NP * L;  // reals per (table, site) row
   extern __shared__ __align__(16) unsigned char cta_smem[];
@@ -776,42 +776,33 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
   const int T = 1 << TSH;  // steps per chunk
   R *rows = reinterpret_cast<R *>(cta_smem);                                   // [2][T][2][ROW]
   R *s_lu = rows + (size_t)4 * T * ROW + (size_t)warp * C * SB;                // [C][SB] of this warp
-  uint32_t *sigx = reinterpret_cast<uint32_t *>(rows + (size_t)4 * T * ROW + (size_t)W * C * SB) + warp * C * WR;
+  // configurations of this warp's chains: [C][W32] words in shared memory (read with a broadcast LDS, flipped by
+  // lane 0), which keeps 4 C registers free for a third chain per warp and lifts the N <= 128 limit
+  uint32_t *sigx = reinterpret_cast<uint32_t *>(rows + (size_t)4 * T * ROW + (size_t)W * C * SB) + warp * C * W32;
   const int64_t chain0 = ((int64_t)blockIdx.x * W + warp) * C;
   const R *Qg = ws;  // global tables
   const V one = P::mk(R(1), R(1));
   // chains of this warp that exist (the others are carried along: every warp takes part in the CTA barriers)
   const int n_valid = a.n_chains - chain0 >= C ? C : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
 
-  // ---- configurations: every lane holds all words of the C chains
-  uint32_t sg[C][WR];
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-#pragma unroll
-    for (int w = 0; w < WR; ++w) {
-      uint32_t v = 0;
-      if (w < W32 && c < n_valid) {
-        if (a.init_random) {
-          u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_INIT};
-          v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
-        } else {
-          v = a.chain_state[(chain0 + c) * W32 + w];
-        }
-        const int nb = N - 32 * w;
-        if (nb < 32) v &= (1u << nb) - 1u;
+  // ---- configurations
+  for (int idx = lane; idx < C * W32; idx += 32) {
+    const int c = idx / W32, w = idx - c * W32;
+    uint32_t v = 0;
+    if (c < n_valid) {
+      if (a.init_random) {
+        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_INIT};
+        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+      } else {
+        v = a.chain_state[(chain0 + c) * W32 + w];
       }
-      sg[c][w] = v;
+      const int nb = N - 32 * w;
+      if (nb < 32) v &= (1u << nb) - 1u;
     }
-  auto sync_sig = [&]() {
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int w = 0; w < WR; ++w) sigx[c * WR + w] = sg[c][w];
-    }
-    __syncwarp();
-  };
+    sigx[idx] = v;
+  }
+  __syncwarp();
+  auto sync_sig = [&]() { __syncwarp(); };
 
   const int n_sweeps = a.n_discard + a.chain_length;
   const uint32_t n_steps = (uint32_t)n_sweeps * (uint32_t)a.sweep_size;
@@ -937,7 +928,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
         V xx[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const R xv = ((sigx[c * WR + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+          const R xv = ((sigx[c * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
           xx[c] = P::mk(xv, xv);
         }
 #pragma unroll
@@ -998,15 +989,15 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
       const uint32_t msk = 1u << (site & 31);
       const int wsel = site >> 5;
 
-      uint32_t bit[C];
+      uint32_t bit[C], word[C];
       R lgn[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        uint32_t v = sg[c][0];
+      for (int c = 0; c < C; ++c) word[c] = sigx[c * W32 + wsel];
 #pragma unroll
-        for (int w = 1; w < WR; ++w) v = (wsel == w) ? sg[c][w] : v;
-        bit[c] = (v >> (site & 31)) & 1u;
+      for (int c = 0; c < C; ++c) {
+        bit[c] = (word[c] >> (site & 31)) & 1u;
         lgn[c] = multiply(Zr[c], Zi[c], slot + bit[c] * ROW, true);
+        if (C > 2) asm volatile("" ::: "memory");  // keep the row loads of the next chain behind this one (registers)
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -1014,13 +1005,13 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
         if (D::accept(lgn[c] - lg[c], thr) && c < n_valid) {
           lg[c] = lgn[c];
           ++n_acc;
-#pragma unroll
-          for (int w = 0; w < WR; ++w) sg[c][w] ^= (wsel == w) ? msk : 0u;
+          if (lane == 0) sigx[c * W32 + wsel] = word[c] ^ msk;
         } else {
           // rejected: multiply back by the other row of the slot (the inverse of the one just applied)
           multiply(Zr[c], Zi[c], slot + (bit[c] ^ 1u) * ROW, false);
         }
       }
+      __syncwarp();  // the flips of this step are visible to the next one
       if ((pos & (uint32_t)(T - 1)) == (uint32_t)(T - 1)) {
         // end of a chunk: the next one has landed everywhere, this one is free for the one after it
         cp_async_wait_all();
@@ -1035,7 +1026,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
 #pragma unroll
       for (int c = 0; c < C; ++c)
         if (c < n_valid)
-          a.samples[((chain0 + c) * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sigx[c * WR + lane];
+          a.samples[((chain0 + c) * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sigx[c * W32 + lane];
     }
   }
   cp_async_wait_all();
@@ -1043,7 +1034,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
   if (lane < W32) {
 #pragma unroll
     for (int c = 0; c < C; ++c)
-      if (c < n_valid) a.chain_state[(chain0 + c) * W32 + lane] = sigx[c * WR + lane];
+      if (c < n_valid) a.chain_state[(chain0 + c) * W32 + lane] = sigx[c * W32 + lane];
   }
   if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
@@ -1059,8 +1050,8 @@ inline void ratio_cta_shape(int64_t n_chains, int C, int sm_count, int maxw, int
   *TSH = w >= 10 ? 3 : 2;
 }
 template <typename R>
-inline size_t ratio_cta_smem(int NP, int C, int W, int TSH) {
-  return ((size_t)4 * (1 << TSH) * 4 * NP * 32 + (size_t)W * C * 128) * sizeof(R) + (size_t)W * C * PIPE_WR_ * 4;
+inline size_t ratio_cta_smem(int NP, int C, int W, int TSH, int W32) {
+  return ((size_t)4 * (1 << TSH) * 4 * NP * 32 + (size_t)W * C * 128) * sizeof(R) + (size_t)W * C * W32 * 4;
 }
 
 template <typename R, int NP, int C, int GL, int MAXW = 16, int MINB = 1>
@@ -1069,7 +1060,7 @@ static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampAr
   int W, TSH;
   ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
   if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning override
-  const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH);
+  const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH, (net->n_visible + 31) >> 5);
   cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);

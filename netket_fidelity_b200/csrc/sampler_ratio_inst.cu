@@ -35,7 +35,7 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
     // small launches (a multi-GPU shard: fewer than ~40 chains per SM) are bound by the latency of one Metropolis
     // step, not by throughput: there the one-chain-per-warp pipelined kernel below, which has the shorter step, wins
     const bool big = a.n_chains >= (int64_t)40 * h->sm_count || getenv("NKFB_RATIO_NOPIPE") || getenv("NKFB_RATIO_FORCECTA");
-    if (a.site_seq != nullptr && big && net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOCTA")) {
+    if (a.site_seq != nullptr && big && !getenv("NKFB_RATIO_NOCTA")) {
       // shared site sequence: CTA-synchronous kernel, C chains per warp (z only: 4 NP words per chain)
       constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
       if (gl_one)

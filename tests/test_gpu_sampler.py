@@ -169,7 +169,7 @@ def kernel_path(monkeypatch):
     return set_
 
 
-@pytest.mark.parametrize("N,M", [(9, 300), (40, 130), (100, 400), (7, 500)])
+@pytest.mark.parametrize("N,M", [(9, 300), (40, 130), (100, 400), (7, 500), (150, 200)])
 @pytest.mark.parametrize("path", ["cta", "pipe", "generic"])
 def test_fp64_multiplicative_kernels_agree_with_restatement(h, algo, kernel_path, N, M, path):
     """The three forms of the multiplicative sampler (sampler_ratio.cuh) on 32-lane shapes, float64: each one
