@@ -55,6 +55,10 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t 
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// NB8: 8-column blocks of the chunk per thread (NN / 16).  The correction of the gate row, sum_s d_s w_eta
+// conj(rho_1) conj(tanh theta'), is accumulated per thread in 8 NB8 registers over ALL its sample tiles and reduced
+// over the 128 rows once at the end (a per-tile reduction costs 40 shuffles + 8 shared atomics per 8 columns).
+template <int NB8>
 __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<float> psi, TcGradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGeom g = a.g;
@@ -117,6 +121,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
   const int64_t t_end = min(n_tiles, t_begin + a.tiles_per_split);
   const int nh = NN / 2;
   const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+  float ccacc[NB8][8];
+#pragma unroll
+  for (int b = 0; b < NB8; ++b)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ccacc[b][q] = 0.f;
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     const int64_t s_base = tile * TC_ROWS;
@@ -171,8 +180,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
           d = ssum - 2.f * (((wd >> (gidx & 31)) & 1u) ? a.s1 : a.s0);
         }
       }
-#pragma unroll 1
-      for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
+#pragma unroll
+      for (int b8 = 0; b8 < NB8; ++b8) {
+        const int c0 = half * nh + 8 * b8;
         float v[8], y[8], cc[8];
         tmem_ld8(tmem_theta + lane_off + (uint32_t)c0, v);
 #pragma unroll
@@ -208,12 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
         *reinterpret_cast<uint4 *>(dst + 2 * y_split_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         if (flip) {  // correction of row idx: sum over the samples of d_s w_eta conj(rho_1) conj(tanh theta')
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float r = cc[q];
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
-            if (lane == 0) atomicAdd(corr + c0 + q, r);
-          }
+          for (int q = 0; q < 8; ++q) ccacc[b8][q] += cc[q];
         }
       }
       fence_async_smem();
@@ -239,6 +244,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
     }
   }
 
+  // ---- correction of the gate row: reduce the per-thread sums over the 128 sample rows
+  if (gate) {
+#pragma unroll
+    for (int b8 = 0; b8 < NB8; ++b8)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float r = ccacc[b8][q];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+        if (lane == 0) atomicAdd(corr + half * nh + 8 * b8 + q, r);
+      }
+  }
   // ---- flush G (TMEM lane = gradient row: spins, then the bias row N) to the fp64 accumulators
   __syncthreads();
   if (g_started) {
@@ -324,9 +341,20 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   int64_t n_splits = std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)h->sm_count / g.NC));
   a.tiles_per_split = (tiles + n_splits - 1) / n_splits;
   n_splits = (tiles + a.tiles_per_split - 1) / a.tiles_per_split;
-  NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(g.NC, (unsigned)n_splits);
-  infid_grad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), a);
+  const int nb8 = g.NN / 16;
+#define NKFB_GRAD_TC_CASE(NB)                                                                                     \
+  case NB:                                                                                                       \
+    NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_grad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)smem));                                                         \
+    infid_grad_tc_kernel<NB><<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), a);                       \
+    break;
+  switch (nb8) {
+    NKFB_GRAD_TC_CASE(1) NKFB_GRAD_TC_CASE(2) NKFB_GRAD_TC_CASE(3) NKFB_GRAD_TC_CASE(4) NKFB_GRAD_TC_CASE(5)
+    NKFB_GRAD_TC_CASE(6) NKFB_GRAD_TC_CASE(7) NKFB_GRAD_TC_CASE(8)
+    default: return 1;  // wider chunks: CUDA-core kernel
+  }
+#undef NKFB_GRAD_TC_CASE
   NKFB_LAUNCHED(h);
   return NKFB_OK;
 }
