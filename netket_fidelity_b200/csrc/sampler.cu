@@ -16,7 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include "sampler_ratio.cuh"
+#include "sampler_composite_ratio.cuh"
 
 namespace nkfb {
 
@@ -117,6 +117,7 @@ __device__ __forceinline__ cx<R> composite_logamp(const NetDev<R> &net, const Op
 template <typename R, int KMAX>
 __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_composite_kernel(NetDev<R> net, SampArgs a) {
   extern __shared__ uint32_t sig_all[];
+  if (!samp_window_ok(a)) return;  // the multiplicative kernel covers this parameter range
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = (M + 31) / 32;
@@ -416,6 +417,53 @@ static int launch_composite(nkfb_handle_t h, const nkfb_rbm_t *net, const SampAr
   return NKFB_OK;
 }
 
+// Ising-type operators: multiplicative kernel (sampler_composite_ratio.cuh) for X <= CR_XMAX, the log-cosh kernel
+// behind it for the rest (same device-side range window as the plain-target kernels, no read-back)
+template <typename R>
+static int dispatch_composite_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs &a, void *ws, size_t ws_bytes,
+                                    cudaStream_t st) {
+  const int N = net->n_visible, M = net->n_hidden;
+  const size_t need = cr_ws_reals(N, M) * sizeof(R);
+  if (ws) {
+    if (ws_bytes < need) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler workspace too small: %zu < %zu bytes", ws_bytes, need);
+  } else {
+    if (h->ws_bytes < need) {
+      if (h->ws) cudaFree(h->ws);
+      h->ws = nullptr;
+      h->ws_bytes = 0;
+      NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws, need));
+      h->ws_bytes = need;
+    }
+    ws = h->ws;
+  }
+  NKFB_CHECK_CUDA(h, cudaMemsetAsync((R *)ws + cr_bound_off(N, M), 0, sizeof(R), st));
+  {
+    const int64_t tot = (int64_t)2 * N * ((M + 1) / 2) + 2 * N + M;
+    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+    prep_composite_ratio<R><<<grid, 256, 0, st>>>(make_netdev<R>(net), (R *)ws, (R)a.s0, (R)a.s1);
+    NKFB_LAUNCHED(h);
+  }
+  a.xbound = reinterpret_cast<const float *>((const R *)ws + cr_bound_off(N, M));
+  a.xlo = -1.0f;
+  a.xhi = CR_XMAX;
+  const int W32 = (N + 31) >> 5, MP = (M + 1) / 2;
+  const size_t per_warp = (size_t)8 * MP * sizeof(R) + (((size_t)W32 * 4 + 15) & ~(size_t)15);
+  const size_t smem = SAMP_WARPS * per_warp;
+  if (smem > 200 * 1024) {
+    a.xbound = nullptr;  // too many hidden units for the shared-memory state: log-cosh kernel only
+    return NKFB_OK;
+  }
+  if (smem > 48 * 1024)
+    NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(sample_composite_ratio_kernel<R>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (a.n_chains + SAMP_WARPS - 1) / SAMP_WARPS;
+  sample_composite_ratio_kernel<R><<<(unsigned)blocks, SAMP_WARPS * 32, smem, st>>>(make_netdev<R>(net), (const R *)ws, a);
+  NKFB_LAUNCHED(h);
+  a.xlo = CR_XMAX;
+  a.xhi = __builtin_inff();
+  return NKFB_OK;
+}
+
 template <typename R>
 static int dispatch_composite(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, cudaStream_t st) {
   const int K = (net->n_hidden + 31) / 32;
@@ -468,6 +516,14 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   if ((uint64_t)(cfg->n_discard + (int64_t)cfg->chain_length) * (uint64_t)cfg->sweep_size >= (1ull << 31))
     NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "more than 2^31 Metropolis steps in one call");
   if (!composite) return dispatch_plain(h, net, a, cfg->workspace, (size_t)cfg->workspace_bytes, st);
+  int algo = h->opt_sampler_algo;
+  if (const char *e = getenv("NKFB_SAMPLER_ALGO")) algo = atoi(e);
+  if (op->kind == NKFB_OP_ISING && algo != 1) {
+    const int rc = net->dtype == NKFB_F32
+                       ? dispatch_composite_ratio<float>(h, net, a, cfg->workspace, (size_t)cfg->workspace_bytes, st)
+                       : dispatch_composite_ratio<double>(h, net, a, cfg->workspace, (size_t)cfg->workspace_bytes, st);
+    if (rc != NKFB_OK) return rc;
+  }
   return net->dtype == NKFB_F32 ? dispatch_composite<float>(h, net, a, st) : dispatch_composite<double>(h, net, a, st);
 }
 

@@ -74,7 +74,11 @@ def test_fp64_chains_continue_across_calls_and_shards(h):
 @pytest.mark.parametrize("U", [oops.Rx(5, 1, 0.8), oops.Hadamard(5, 0),
                                oops.IsingPropagator(5, oops.chain_edges(5), 1.0, 1.0, 0.2)])
 @pytest.mark.parametrize("M", [5, 40])
-def test_fp64_composite_trajectories(h, U, M):
+@pytest.mark.parametrize("sampler", [1, 2])
+def test_fp64_composite_trajectories(h, algo, U, M, sampler):
+    """sampler 1: complex log-cosh kernel; 2: for Ising-type operators the multiplicative kernel
+    (sampler_composite_ratio.cuh), which must accept exactly the same proposals in float64."""
+    algo(sampler)
     N = 5
     p = _net(N, M, 31, 0.3)
     ref, fin, nacc_ref = metropolis_local_b200(p, 5, 3, 1, N, seed=99, U=U)
@@ -254,10 +258,47 @@ def test_fp32_samplers_saturated_hidden_units(h, algo, B, sampler):
 @pytest.mark.parametrize("U", [oops.Rx(6, 2, 0.9), oops.Ry(6, 0, 0.7), oops.Hadamard(6, 5),
                                oops.IsingPropagator(6, oops.chain_edges(6), 1.0, 1.0, 0.1)])
 @pytest.mark.parametrize("cd", [torch.complex64, torch.complex128])
-def test_composite_sampler_matches_exact_distribution(h, U, cd):
+@pytest.mark.parametrize("sampler", [1, 2])
+def test_composite_sampler_matches_exact_distribution(h, algo, U, cd, sampler):
+    algo(sampler)
     N, M = 6, 12
     p = _net(N, M, 5, 0.3)
     got, _, _ = _run(h, p, cd, 2048, 64, 30, N, 4242, U=U)
+    x = unpack_np(got.reshape(-1, got.shape[-1]), N)
+    counts = np.bincount(states_to_numbers(x), minlength=2 ** N)
+    pe = exact_distribution(make_logfun(p, U), N)
+    keep = pe * counts.sum() > 50
+    z = _z_scores(counts, pe, inflate=6.0)
+    assert np.max(np.abs(z[keep])) < 5.0, np.max(np.abs(z[keep]))
+
+
+@pytest.mark.parametrize("N,M,std", [(12, 30, 0.15), (40, 80, 0.02), (33, 70, 0.05)])
+def test_fp64_ising_composite_kernels_agree_on_longer_runs(h, algo, N, M, std):
+    """Ising-type propagator targets at the C3 shape and beyond one 32-lane round of connected configurations:
+    the multiplicative kernel and the log-cosh kernel emit identical float64 trajectories (chains continued over
+    two calls, non-zero chain offset)."""
+    U = oops.IsingPropagator(N, oops.chain_edges(N), 1.0, 1.0, 0.01)
+    p = _net(N, M, 77, std)
+    out = {}
+    for sampler in (1, 2):
+        algo(sampler)
+        a, st, na = _run(h, p, torch.complex128, 6, 3, 1, N, 123, U=U, chain_offset=3)
+        b, st, nb = _run(h, p, torch.complex128, 6, 2, 0, N, 123, U=U, chain_offset=3, step_offset=4 * N, state=st)
+        out[sampler] = (a, b, na + nb)
+    np.testing.assert_array_equal(out[1][0], out[2][0])
+    np.testing.assert_array_equal(out[1][1], out[2][1])
+    assert out[1][2] == out[2][2]
+
+
+def test_fp32_ising_composite_saturated_units(h, algo):
+    """Parameters beyond the range of the multiplicative composite kernel (X > 3): the log-cosh kernel behind it
+    takes over; the distribution is still exact."""
+    N, M = 6, 12
+    p = _net(N, M, 5, 0.2)
+    p = RBMParams(p.kernel, p.bias + 6.0 * np.where(np.arange(M) % 2 == 0, 1.0, -1.0), p.visible_bias)
+    U = oops.IsingPropagator(N, oops.chain_edges(N), 1.0, 1.0, 0.1)
+    algo(2)
+    got, _, _ = _run(h, p, torch.complex64, 2048, 64, 30, N, 4242, U=U)
     x = unpack_np(got.reshape(-1, got.shape[-1]), N)
     counts = np.bincount(states_to_numbers(x), minlength=2 ** N)
     pe = exact_distribution(make_logfun(p, U), N)
