@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
     for (int side = 0; side < 2; ++side) {
       const uint32_t *packed = side == 0 ? a.sigma : a.eta;
       const bool flip = gate && side == 1;
-      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1);
+      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, true);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();

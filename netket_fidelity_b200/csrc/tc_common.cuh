@@ -152,29 +152,55 @@ static __global__ void tc_prep_kernel(NetDev<float> net, TcGeom g, __nv_bfloat16
   }
 }
 
-// X tile in the canonical K-major no-swizzle layout [kc][row][8] bf16
+// X tile in the canonical K-major no-swizzle layout [kc][row][8] bf16.
+// TC_THREADS = 2 TC_ROWS: thread t always serves row t % 128 and the 8-spin groups kc = t / 128, t / 128 + 2, ...;
+// for N <= 128 it reads its row's packed words ONCE (they used to be re-read per group: 7 dependent L2 round
+// trips per tile at C4, 13 % of the estimator's time on the long scoreboard) and cuts the groups out of registers.
+// (single_load = false keeps the per-group loads: with two CTAs per SM the estimator hides that latency and the
+// shorter code wins there -- measured.)
 __device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_t *packed, int64_t s_base, int64_t S,
-                                                const TcGeom &g, float s0, float s1) {
+                                                const TcGeom &g, float s0, float s1, bool single_load = false) {
   const int W32 = (g.N + 31) >> 5;
   const uint16_t b0 = __bfloat16_as_ushort(__float2bfloat16_rn(s0)), b1 = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
-  for (int idx = threadIdx.x; idx < g.KC * TC_ROWS; idx += TC_THREADS) {
-    const int kc = idx / TC_ROWS, r = idx - kc * TC_ROWS;
-    const int64_t gs = s_base + r;
-    uint32_t bits = 0;
-    const int k0 = kc * 8;
-    if (gs < S && k0 < g.N) bits = (packed[gs * W32 + (k0 >> 5)] >> (k0 & 31)) & 0xFFu;
+  auto emit = [&](int idx, int k0, uint32_t bits, bool live) {
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint32_t lo16 = 0, hi16 = 0;
       const int ka = k0 + 2 * q, kb = ka + 1;
-      if (gs < S) {
+      if (live) {
         lo16 = ka < g.N ? (((bits >> (2 * q)) & 1u) ? b1 : b0) : (ka == g.N ? 0x3F80u : 0u);
         hi16 = kb < g.N ? (((bits >> (2 * q + 1)) & 1u) ? b1 : b0) : (kb == g.N ? 0x3F80u : 0u);
       }
       w[q] = lo16 | (hi16 << 16);
     }
     *reinterpret_cast<uint4 *>(As + (size_t)idx * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  if (single_load && W32 <= 4 && g.KC <= 16) {
+    const int r = threadIdx.x & (TC_ROWS - 1), kc0 = threadIdx.x / TC_ROWS;
+    const int64_t gs = s_base + r;
+    const bool live = gs < S;
+    uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      if (live && w < W32) wd[w] = __ldg(packed + gs * W32 + w);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {  // kc = kc0 + 2 m, first spin 8 kc0 + 16 m: packed word m / 2
+      const int kc = kc0 + 2 * m;
+      if (kc < g.KC) {
+        const int k0 = kc * 8;
+        emit(kc * TC_ROWS + r, k0, (wd[m >> 1] >> (k0 & 31)) & 0xFFu, live);
+      }
+    }
+    return;
+  }
+  for (int idx = threadIdx.x; idx < g.KC * TC_ROWS; idx += TC_THREADS) {
+    const int kc = idx / TC_ROWS, r = idx - kc * TC_ROWS;
+    const int64_t gs = s_base + r;
+    uint32_t bits = 0;
+    const int k0 = kc * 8;
+    if (gs < S && k0 < g.N) bits = (packed[gs * W32 + (k0 >> 5)] >> (k0 & 31)) & 0xFFu;
+    emit(idx, k0, bits, gs < S);
   }
 }
 
