@@ -50,9 +50,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def n_in(self, window):
+        return sum(1 for t, _ in self.lines if window[0] <= t <= window[1])
+
+    def stop(self, window=None):
+        """Summary of the samples that arrived inside `window` (host wall-clock of the timed region, possibly
+        extended by the caller with more steps of the same workload when the region is shorter than nvidia-smi's
+        100 ms period)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -62,7 +68,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for tstamp, ln in self.lines:
+            if window is not None and not (window[0] <= tstamp <= window[1]):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -178,20 +186,21 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # started before the warm-up so that nvidia-smi is already reporting when timing starts
     for _ in range(args.warmup):
         flush.zero_()
         eng.step(specs["psi"], specs["phi"])
     barrier()
 
     # ------------------------------------------------------------ device-resident timing
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     samp_ev = [(ev(), ev()) for _ in range(args.steps)]
     est_ev = [(ev(), ev(), ev()) for _ in range(args.steps)]
     launches0 = h.launches
     barrier()
     e0, e1 = ev(), ev()
+    t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         flush.zero_()
@@ -207,12 +216,25 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    clk = clocks.stop() if rank == 0 else None
+    s = sums.cpu().numpy()          # result of the last TIMED step (the extension below runs further steps)
+    infid = 1.0 - s[0] / s[4]
+    acc_rate = eng.n_accepted.sum().item() / (2.0 * eng.local_chains * (5 + w["chain_length"]) * N * eng.steps_done)
+    # clocks under load: samples that arrived during the timed region; when it is shorter than nvidia-smi's period
+    # (multi-GPU runs: tens of ms) every rank keeps running the same step, untimed, until rank 0 has two samples
+    t_wall1 = time.time()
+    for _ in range(200):
+        need = torch.tensor([1 if (rank == 0 and clocks.n_in((t_wall0, t_wall1)) < 2) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(need, 0)
+        if int(need.item()) == 0:
+            break
+        eng.step(specs["psi"], specs["phi"])
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+    clk = clocks.stop((t_wall0, t_wall1)) if rank == 0 else None
     samp_ms = sum(a.elapsed_time(b) for a, b in samp_ev) / args.steps   # two sampler launches per step
     fwd_ms = sum(a.elapsed_time(b) for a, b, c in est_ev) / args.steps
     grad_ms = sum(b.elapsed_time(c) for a, b, c in est_ev) / args.steps  # includes the 64-byte all-reduce when N > 1
-    s = sums.cpu().numpy()
-    infid = 1.0 - s[0] / s[4]
 
     # ------------------------------------------------------------ end-to-end through the public API (host buffers)
     # psi.parameters <- pinned host copy (H2D), reset both states, psi.expect_and_grad(I_op) [sampling of both
@@ -319,8 +341,7 @@ def run_b200(args):
                          "traffic_note": "dram__bytes_read+write of one sampler launch from profiles/r01_ncu_top_kernels.md "
                                          "(1.45 MB read + 256 B written: tables and packed samples stay in L2)",
                          "other_kernels": other},
-            "result": {"infidelity": infid, "acceptance": (eng.n_accepted.sum().item() /
-                                                            (2.0 * eng.local_chains * sweeps * N * eng.steps_done))},
+            "result": {"infidelity": infid, "acceptance": acc_rate},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle.baseline import make_workload as omw, cpu_step
