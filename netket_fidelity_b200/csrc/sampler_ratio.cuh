@@ -723,6 +723,24 @@ static int launch_ratio_pipe(nkfb_handle_t h, const nkfb_rbm_t *net, const SampA
   return NKFB_OK;
 }
 
+// z <- z q on a pair of units with the results TIED to the registers of z (inline PTX, "+l" operands): with plain
+// C++ the compiler keeps part of the new z in temporaries and reconciles the accept / multiply-back paths with a
+// dozen register moves per chain and step.
+__device__ __forceinline__ void cmul_inplace(float2 &zr, float2 &zi, float2 ql, float2 qh) {
+  const float2 s = __fmul2_rn(zr, qh);
+  const float2 t = __fmul2_rn(zi, qh);
+  unsigned long long &ZR = reinterpret_cast<unsigned long long &>(zr), &ZI = reinterpret_cast<unsigned long long &>(zi);
+  const unsigned long long QL = reinterpret_cast<const unsigned long long &>(ql);
+  const float2 nt = make_float2(-t.x, -t.y);
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ZI) : "l"(QL), "l"(reinterpret_cast<const unsigned long long &>(s)));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ZR) : "l"(QL), "l"(reinterpret_cast<const unsigned long long &>(nt)));
+}
+__device__ __forceinline__ void cmul_inplace(double2 &zr, double2 &zi, double2 ql, double2 qh) {
+  const double2 s = make_double2(zr.x * qh.x, zr.y * qh.y), t = make_double2(zi.x * qh.x, zi.y * qh.y);
+  zi = make_double2(fma(zi.x, ql.x, s.x), fma(zi.y, ql.y, s.y));
+  zr = make_double2(fma(zr.x, ql.x, -t.x), fma(zr.y, ql.y, -t.y));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // CTA-synchronous form for the shared site sequence (site_mode 0): the hot form of the multiplicative sampler.
 //
@@ -848,7 +866,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
 #pragma unroll
     for (int gq = 0; gq < NG; ++gq) {
       constexpr int GS = GL;
-      V qlo[GS], qhi[GS], t[GS], u[GS], m[GS];
+      V qlo[GS], qhi[GS], m[GS];
 #pragma unroll
       for (int i = 0; i < GS; ++i) {
         const int p = gq * GL + i;
@@ -861,18 +879,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
 #pragma unroll
       for (int i = 0; i < GS; ++i) {
         const int p = gq * GL + i;
-        if (p < NP) {
-          t[i] = P::mul(zi[p], qhi[i]);
-          u[i] = P::mul(zi[p], qlo[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < GS; ++i) {
-        const int p = gq * GL + i;
-        if (p < NP) {
-          zi[p] = P::fma(zr[p], qhi[i], u[i]);
-          zr[p] = P::fma(zr[p], qlo[i], neg2_(t[i]));
-        }
+        if (p < NP) cmul_inplace(zr[p], zi[p], qlo[i], qhi[i]);
       }
       if (want_log) {
 #pragma unroll
