@@ -268,6 +268,9 @@ static int ratio_pick_L(int M, bool f32) {
       bestL = L;
     }
   }
+  // the full-warp shapes have the pipelined / CTA-synchronous kernels: take them up to 30 % more padded work
+  const int NP32 = ratio_pairs(M, 32);
+  if (bestL != 0 && bestL != 32 && NP32 <= (f32 ? 16 : 8) && 10 * (64 * NP32) <= 13 * bestWork) bestL = 32;
   return bestL;
 }
 

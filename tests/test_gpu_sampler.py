@@ -235,14 +235,15 @@ def test_sampler_matches_exact_distribution(h, algo, N, M, cd, site_mode, sample
 
 @pytest.mark.parametrize("B", [0.0, 4.0, 14.0])
 @pytest.mark.parametrize("sampler", [1, 2])
-def test_fp32_samplers_saturated_hidden_units(h, algo, B, sampler):
+@pytest.mark.parametrize("M", [24, 100])
+def test_fp32_samplers_saturated_hidden_units(h, algo, B, sampler, M):
     """Single precision with hidden biases +-B: X = max_j (|Re b_j| + sum_i |Re W_ij|) = 1.6 / 5.6 / 15.6 falls
     in the first (one log per 4 pairs), second (one log per pair) and third (additive kernel) range window of
     the multiplicative sampler; z = exp(-2 theta) spans e^{+-2X}.  The distribution itself stays broad (large
     biases saturate cosh), so the chains mix within a sweep and the z-scores are meaningful."""
     algo(sampler)
-    N, M = 10, 24
-    p = _net(N, M, 21, 0.15)
+    N = 10                                 # M = 24: lane-group kernel; M = 100: 32-lane (pipelined) kernels
+    p = _net(N, M, 21, 0.15 * (24.0 / M) ** 0.5)
     p = RBMParams(p.kernel, p.bias + B * np.where(np.arange(M) % 2 == 0, 1.0, -1.0), p.visible_bias)
     X = np.max(np.abs(p.bias.real) + np.abs(p.kernel.real).sum(0))
     assert {0.0: X < 2.6, 4.0: 2.8 < X < 10.6, 14.0: X > 10.8}[B], X
@@ -305,3 +306,17 @@ def test_fp32_ising_composite_saturated_units(h, algo):
     keep = pe * counts.sum() > 50
     z = _z_scores(counts, pe, inflate=6.0)
     assert np.max(np.abs(z[keep])) < 5.0, np.max(np.abs(z[keep]))
+
+
+def test_long_calls_fall_back_from_the_site_table(h, algo):
+    """More Metropolis steps in one call than the site table of the CTA-synchronous kernel holds (65536): the
+    dispatcher uses the pipelined kernel; float64 samples equal those of the additive kernel."""
+    N, M = 40, 130
+    p = _net(N, M, 8, 0.05)
+    n_sweeps = 1700                      # 68000 steps
+    algo(1)
+    a, sa, na = _run(h, p, torch.complex128, 3, n_sweeps, 0, N, 11)
+    algo(2)
+    b, sb, nb = _run(h, p, torch.complex128, 3, n_sweeps, 0, N, 11)
+    np.testing.assert_array_equal(a, b)
+    assert na == nb
