@@ -473,10 +473,9 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
   const R *A0 = ws + (size_t)8 * N * NP * L;
   const V one = P::mk(R(1), R(1));
 
-  // ---- configuration: every lane holds all words
-  uint32_t sg[WR];
-#pragma unroll
-  for (int w = 0; w < WR; ++w) {
+  // ---- configuration: WR words in shared memory (read with a broadcast LDS, flipped by lane 0; kept in registers
+  // they turned into a local-memory array behind a jump table)
+  for (int w = lane; w < WR; w += 32) {
     uint32_t v = 0;
     if (w < W32) {
       if (a.init_random) {
@@ -488,22 +487,11 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
       const int nb = N - 32 * w;
       if (nb < 32) v &= (1u << nb) - 1u;
     }
-    sg[w] = v;
+    sig[w] = v;
   }
-  auto spin_bit = [&](int st) -> uint32_t {
-    uint32_t v = sg[0];
-#pragma unroll
-    for (int w = 1; w < WR; ++w) v = ((st >> 5) == w) ? sg[w] : v;
-    return (v >> (st & 31)) & 1u;
-  };
-  auto sync_sig = [&]() {
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int w = 0; w < WR; ++w) sig[w] = sg[w];
-    }
-    __syncwarp();
-  };
+  __syncwarp();
+  auto spin_bit = [&](int st) -> uint32_t { return (sig[st >> 5] >> (st & 31)) & 1u; };
+  auto sync_sig = [&]() { __syncwarp(); };
 
   const int n_sweeps = a.n_discard + a.chain_length;
   const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));
@@ -677,12 +665,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
         lg = lgn;
         cur ^= 1u;
         ++n_acc;
-        {
-          const uint32_t msk = 1u << (site & 31);
-#pragma unroll
-          for (int w = 0; w < WR; ++w)
-            if ((site >> 5) == w) sg[w] ^= msk;
-        }
+        if (lane == 0) sig[site >> 5] ^= 1u << (site & 31);
         if (nsite == site) {
           // the next proposal flips the same spin back: its row is the inverse of the one requested above
           nthr_r = nlogu - (nbit ? na0 : -na0);
@@ -697,6 +680,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
       }
       site = nsite;
       thr = D::threshold(nthr_r);
+      __syncwarp();  // the flip of this step is visible to the next one
     }
 
     // ---- sweep boundary: emit the configuration
