@@ -212,6 +212,22 @@ def run_b200(args):
     barrier()
     launches = h.launches - launches0
     ms = e0.elapsed_time(e1)
+    graph_ms = None
+    if args.graph and world == 1:
+        # the same K steps replayed from ONE captured CUDA graph per step (engine.capture_graph): what the step
+        # costs once the ~18 launches and the Python in between are out of the way (small workloads)
+        eng.capture_graph(specs["psi"], specs["phi"])
+        for _ in range(3):
+            eng.step(specs["psi"], specs["phi"])
+        torch.cuda.synchronize()
+        g0, g1 = ev(), ev()
+        g0.record()
+        for i in range(args.steps):
+            flush.zero_()
+            sums, L, grad = eng.step(specs["psi"], specs["phi"])
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,6 +358,9 @@ def run_b200(args):
                                          "(1.45 MB read + 256 B written: tables and packed samples stay in L2)",
                          "other_kernels": other},
             "result": {"infidelity": infid, "acceptance": acc_rate},
+            **({"cuda_graph": {"ms_per_step": graph_ms, "value": S_total / (graph_ms * 1e-3), "unit": UNIT,
+                               "note": "one captured CUDA graph per step, replayed (not the headline `value`)"}}
+               if graph_ms else {}),
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle.baseline import make_workload as omw, cpu_step
@@ -369,6 +388,7 @@ def main():
     ap.add_argument("--ref-chains", type=int, default=16)
     ap.add_argument("--ref-chain-length", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

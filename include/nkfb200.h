@@ -96,6 +96,9 @@ typedef struct {
   void *workspace;         /* device scratch of >= nkfb_sample_workspace_bytes() bytes, or NULL to use the
                               handle's own buffer (then calls on different streams must not overlap) */
   uint64_t workspace_bytes;
+  const uint64_t *step_offset_dev; /* optional device counter ADDED to step_offset when the kernels start: lets a
+                                      captured CUDA graph of a whole step be replayed (the host-side value is
+                                      frozen at capture time); NULL otherwise */
 } nkfb_sample_cfg_t;
 
 /* ---- lifecycle ---------------------------------------------------------- */

@@ -50,7 +50,8 @@ class SampleCfgT(C.Structure):
                 ("sweep_size", C.c_int32), ("site_mode", C.c_int32), ("seed", C.c_uint64),
                 ("chain_offset", C.c_uint64), ("step_offset", C.c_uint64),
                 ("local_states", C.c_double * 2), ("init_random", C.c_int32), ("reserved", C.c_int32),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+                ("step_offset_dev", C.c_void_p)]
 
 
 _lib = None
@@ -277,7 +278,8 @@ class Handle:
     # ---------------------------------------------------------------- sampler
     def sample(self, net: RbmSpec, chain_state, chain_length, n_discard, sweep_size, seed, local_states,
                op: OpSpec | None = None, chain_offset=0, step_offset=0, site_mode=0, init_random=False,
-               n_accepted=None, out=None, workspace=None):
+               n_accepted=None, out=None, workspace=None, step_offset_dev=None):
+        """step_offset_dev: optional device int64[1] added to step_offset by the kernels (CUDA-graph replays)."""
         n_chains, W32 = chain_state.shape
         if out is None:
             out = torch.empty((n_chains, chain_length, W32), dtype=torch.int32, device=chain_state.device)
@@ -290,6 +292,8 @@ class Handle:
         if workspace is not None:
             cfg.workspace = workspace.data_ptr()
             cfg.workspace_bytes = workspace.numel() * workspace.element_size()
+        if step_offset_dev is not None:
+            cfg.step_offset_dev = step_offset_dev.data_ptr()
         ns = net.struct()
         os_ = op.struct() if op is not None else None
         self._check(self.lib.nkfb_sample(self.h, C.byref(ns), C.byref(os_) if os_ is not None else None,

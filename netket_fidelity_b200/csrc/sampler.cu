@@ -118,6 +118,7 @@ template <typename R, int KMAX>
 __global__ void __launch_bounds__(SAMP_WARPS * 32) sample_composite_kernel(NetDev<R> net, SampArgs a) {
   extern __shared__ uint32_t sig_all[];
   if (!samp_window_ok(a)) return;  // the multiplicative kernel covers this parameter range
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = (M + 31) / 32;
@@ -308,10 +309,10 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
     const unsigned grid = (unsigned)((n_steps + 255) / 256);
     if (f32)
       prep_site_seq<float><<<grid, 256, 0, st>>>((const float *)ws + a0_off, N, a.k0, a.k1, a.step_offset,
-                                                 (uint32_t)n_steps, site_seq, (float *)a0_seq);
+                                                 a.step_offset_dev, (uint32_t)n_steps, site_seq, (float *)a0_seq);
     else
       prep_site_seq<double><<<grid, 256, 0, st>>>((const double *)ws + a0_off, N, a.k0, a.k1, a.step_offset,
-                                                  (uint32_t)n_steps, site_seq, (double *)a0_seq);
+                                                  a.step_offset_dev, (uint32_t)n_steps, site_seq, (double *)a0_seq);
     NKFB_LAUNCHED(h);
     a.site_seq = site_seq;
     a.a0_seq = a0_seq;
@@ -508,6 +509,7 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   a.k1 = (uint32_t)(cfg->seed >> 32);
   a.chain_offset = cfg->chain_offset;
   a.step_offset = cfg->step_offset;
+  a.step_offset_dev = (const unsigned long long *)cfg->step_offset_dev;
   a.s0 = cfg->local_states[0];
   a.s1 = cfg->local_states[1];
   a.chain_state = chain_state;

@@ -21,11 +21,17 @@ struct SampArgs {
   // xlo < *xbound <= xhi, so that exactly one of the kernels launched back to back does the work
   const float *xbound;
   float xlo, xhi;
+  // optional device-resident step counter added to step_offset (CUDA-graph replays: the host value is frozen)
+  const unsigned long long *step_offset_dev;
   // site_mode 0: proposal sites / A_site of the steps of this call (prep_site_seq), or null
   const int *site_seq;
   const void *a0_seq;
   OpDev op;
 };
+
+__device__ __forceinline__ void samp_resolve_offset(SampArgs &a) {
+  if (a.step_offset_dev) a.step_offset += *a.step_offset_dev;
+}
 
 __device__ __forceinline__ bool samp_window_ok(const SampArgs &a) {
   if (a.xbound == nullptr) return true;

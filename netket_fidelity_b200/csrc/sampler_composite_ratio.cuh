@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, sizeof(R) == 4 ? 7 : 3) sampl
   using V4 = V4T<R>;
   extern __shared__ __align__(16) unsigned char cr_smem[];
   if (!samp_window_ok(a)) return;
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5, MP = (M + 1) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t per_warp = ((size_t)8 * MP) * sizeof(R) + (((size_t)W32 * 4 + 15) & ~(size_t)15);

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_plain_kernel(NetDe
   constexpr int SB = 4 * BLK;    // MH steps per RNG batch
   extern __shared__ uint32_t sig_all[];
   if (!samp_window_ok(a)) return;  // another kernel of the same call covers this parameter range
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / L, l = lane % L;

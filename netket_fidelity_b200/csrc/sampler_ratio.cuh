@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_kernel(NetDe
   constexpr int SB = 4 * BLK;    // MH steps per RNG batch
   extern __shared__ uint32_t sig_all[];
   if (!samp_window_ok(a)) return;
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / L, l = lane % L;
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(SAMP_WARPS * 32, MB) sample_ratio_pipe_kernel(
   constexpr int NG = (NP + GL - 1) / GL;  // logarithms per step
   extern __shared__ __align__(16) unsigned char pipe_smem[];
   if (!samp_window_ok(a)) return;
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = lane;
@@ -741,10 +743,11 @@ __device__ __forceinline__ void cmul_inplace(double2 &zr, double2 &zi, double2 q
 constexpr int SITE_SEQ_CAP = 1 << 16;  // steps per call covered by the site table in the workspace
 
 template <typename R>
-__global__ void prep_site_seq(const R *A0, int N, uint32_t k0, uint32_t k1, uint64_t step_offset, uint32_t n_steps,
-                              int *site_seq, R *a0_seq) {
+__global__ void prep_site_seq(const R *A0, int N, uint32_t k0, uint32_t k1, uint64_t step_offset,
+                              const unsigned long long *step_offset_dev, uint32_t n_steps, int *site_seq, R *a0_seq) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_steps) return;
+  if (step_offset_dev) step_offset += *step_offset_dev;
   const uint64_t pos = step_offset + s, blk = pos >> 2;
   u32x4 c2 = {(uint32_t)blk, (uint32_t)(blk >> 32), 0u, (uint32_t)TAG_SITE_SHARED};
   const int site = (int)__umulhi(sel4(philox4x32_10(c2, k0, k1), (int)(pos & 3)), (uint32_t)N);
@@ -772,6 +775,7 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
   constexpr int ROW = 4 * NP * L;  // reals per (table, site) row
   extern __shared__ __align__(16) unsigned char cta_smem[];
   if (!samp_window_ok(a)) return;  // uniform over the grid: taken before any barrier
+  samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int l = lane;

@@ -90,6 +90,10 @@ class InfidelityStep:
         self.ws_psi = self.ws_phi = None
         self.steps_done = 0
         self.initialised = False
+        # CUDA-graph replay of a whole step (single rank): the Metropolis step counter lives on the device
+        self._step_dev = None
+        self._graph = None
+        self._graph_out = None
         self.sweep = cfg.sweep_size if cfg.sweep_size is not None else N
         self.last = {}
 
@@ -97,7 +101,10 @@ class InfidelityStep:
     def sample(self, psi: nv.RbmSpec, phi: nv.RbmSpec):
         cfg = self.cfg
         init = not self.initialised
-        step_offset = self.steps_done * (cfg.n_discard + cfg.chain_length) * self.sweep
+        steps_per_call = (cfg.n_discard + cfg.chain_length) * self.sweep
+        step_offset = self.steps_done * steps_per_call
+        if self._step_dev is not None:
+            step_offset = 0          # the device counter carries it (frozen host values inside a captured graph)
         if self.ws_psi is None:
             self.ws_psi, self.ws_phi = self.h.sample_workspace(psi), self.h.sample_workspace(phi)
         main = torch.cuda.current_stream(self.dev)
@@ -108,14 +115,17 @@ class InfidelityStep:
         self.h.sample(psi, self.state_psi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
                       cfg.local_states, op=None, chain_offset=self.chain_offset, step_offset=step_offset,
                       site_mode=cfg.site_mode, init_random=init, n_accepted=self.n_accepted[0:1], out=self.sigma,
-                      workspace=self.ws_psi)
+                      workspace=self.ws_psi, step_offset_dev=self._step_dev)
         with torch.cuda.stream(side):
             self.h.sample(phi, self.state_phi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
                           cfg.local_states, op=self.op_target, chain_offset=cfg.n_chains + self.chain_offset,
                           step_offset=step_offset, site_mode=cfg.site_mode, init_random=init,
-                          n_accepted=self.n_accepted[1:2], out=self.eta, workspace=self.ws_phi)
+                          n_accepted=self.n_accepted[1:2], out=self.eta, workspace=self.ws_phi,
+                          step_offset_dev=self._step_dev)
         if not self.single_stream:
             main.wait_stream(self.side_stream)
+        if self._step_dev is not None:
+            self._step_dev += steps_per_call
         self.initialised = True
         self.steps_done += 1
 
@@ -149,5 +159,32 @@ class InfidelityStep:
 
     def step(self, psi, phi, return_grad=True):
         """reset + sample both families + estimator (+ gradient): the unit bench.py times."""
+        if self._graph is not None:
+            self._graph.replay()
+            self.steps_done += 1
+            return self._graph_out
         self.sample(psi, phi)
         return self.estimate(psi, phi, return_grad)
+
+    def capture_graph(self, psi, phi, return_grad=True):
+        """Capture one whole step (both sampler launches on their two streams, estimator, gradient, finalize) in a
+        CUDA graph; later `step()` calls replay it: one launch instead of ~18, which is what small problems
+        (BASELINE C1 / C2: a step is a few hundred microseconds of kernels) are bound by.  The parameters are read
+        from the buffers of `psi` / `phi` at replay time, so in-place optimiser updates are seen; the Metropolis
+        step counter lives on the device (nkfb_sample_cfg_t.step_offset_dev).  Single rank only."""
+        if self.world != 1:
+            raise RuntimeError("capture_graph: single-rank only (the all-reduces are not captured)")
+        if self._graph is not None:
+            return
+        if not self.initialised:
+            self.step(psi, phi, return_grad)           # random initial configurations, workspaces
+        steps_per_call = (self.cfg.n_discard + self.cfg.chain_length) * self.sweep
+        self._step_dev = torch.full((1,), self.steps_done * steps_per_call, dtype=torch.int64, device=self.dev)
+        self.step(psi, phi, return_grad)               # eager warm-up with the device counter
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.sample(psi, phi)
+            out = self.estimate(psi, phi, return_grad)
+        self.steps_done -= 1                           # the capture recorded a step, it did not run one
+        self._graph, self._graph_out = g, out

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     from netket_fidelity_b200 import _native as nv
     assert ctypes.sizeof(nv.RbmT) == 40
     assert ctypes.sizeof(nv.OpT) == 8 + 64 + 48 + 8 + 8
-    assert ctypes.sizeof(nv.SampleCfgT) == 8 + 16 + 24 + 16 + 8 + 16
+    assert ctypes.sizeof(nv.SampleCfgT) == 8 + 16 + 24 + 16 + 8 + 16 + 8
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -152,3 +152,25 @@ def test_renyi2_full_size_symmetry_and_product_state():
     vs.reset()
     s0 = vs.expect(nkf.renyi2.Renyi2EntanglementEntropy(hi, A))
     assert abs(s0.mean) < 1e-5, s0
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_cuda_graph_replay_equals_eager_steps(name):
+    """A whole step captured in a CUDA graph (engine.InfidelityStep.capture_graph; the Metropolis step counter on the
+    device) replays to exactly the eager results, step after step."""
+    w = make_workload(name)
+    psi, phi = _specs(w, std=0.1)
+    eager, graphed = _engine(w, seed=5), _engine(w, seed=5)
+    ref = []
+    for _ in range(5):
+        sums, L, grad = eager.step(psi, phi)
+        ref.append((sums.clone(), grad.clone(), eager.sigma.clone()))
+    graphed.step(psi, phi)                 # step 0 eagerly (random initial configurations)
+    graphed.capture_graph(psi, phi)        # runs step 1 eagerly as its warm-up, captures
+    assert torch.equal(graphed.sigma, ref[1][2])
+    for k in range(2, 5):
+        sums, L, grad = graphed.step(psi, phi)
+        torch.cuda.synchronize()
+        assert torch.equal(graphed.sigma, ref[k][2])
+        np.testing.assert_allclose(sums.cpu().numpy(), ref[k][0].cpu().numpy(), rtol=1e-12)
+        assert torch.allclose(grad, ref[k][1], rtol=1e-5, atol=1e-8)
