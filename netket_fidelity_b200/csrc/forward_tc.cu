@@ -62,6 +62,44 @@ struct LcAcc {
   __device__ __forceinline__ cx<float> value() const { return mk<float>(sx + lr, sy + li); }
 };
 
+// Epilogue of one (chunk, tile, side): this thread's row, columns [c_begin, c_end) of the chunk (multiples of 8).
+// FLIP: also accumulate the configuration with the gate site flipped (theta + d W[idx, :]);  FULL: every column of
+// the range is a real hidden-unit column (no per-unit bound test; false only for the last chunk).
+// Blocks of 8 units (16 columns) with one flush of the running products each, as before (same numerics).
+template <bool FLIP, bool FULL>
+__device__ __forceinline__ void fwd_epilogue(LcAcc &A0, LcAcc &A1, uint32_t trow, int c_begin, int c_end, int col0,
+                                             int cols, const float *wg, float d) {
+  float p0r = 1.f, p0i = 0.f, p1r = 1.f, p1i = 0.f;
+  int c0 = c_begin;
+#pragma unroll 1
+  for (; c0 + 16 <= c_end; c0 += 16) {
+    float v[16];
+    tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (FULL || col0 + c0 + 2 * u < cols) {
+        A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
+        if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
+      }
+    }
+    A0.flush(p0r, p0i);
+    if (FLIP) A1.flush(p1r, p1i);
+  }
+  if (c0 < c_end) {  // a last block of 8 columns
+    float v[8];
+    tmem_ld8(trow + (uint32_t)c0, v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (FULL || col0 + c0 + 2 * u < cols) {
+        A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
+        if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
+      }
+    }
+    A0.flush(p0r, p0i);
+    if (FLIP) A1.flush(p1r, p1i);
+  }
+}
+
 struct TcFwdArgs {
   OpDev op1, op2, op4;
   const uint32_t *sigma, *eta;
@@ -182,29 +220,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
             LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
             const int nh = g.NN / 2;  // columns per half (multiple of 8)
             const uint32_t trow = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16);
-            int cnt = 0;
-            float p0r = 1.f, p0i = 0.f, p1r = 1.f, p1i = 0.f;
-#pragma unroll 1
-            for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
-              float v[8];
-              tmem_ld8(trow + (uint32_t)c0, v);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int col = chunk * g.NN + c0 + 2 * u;
-                if (col < cols) {
-                  A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
-                  if (flip)
-                    A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
-                }
-              }
-              if ((++cnt & 1) == 0) {
-                A0.flush(p0r, p0i);
-                if (flip) A1.flush(p1r, p1i);
-              }
-            }
-            if (cnt & 1) {
-              A0.flush(p0r, p0i);
-              if (flip) A1.flush(p1r, p1i);
+            const int cb = half * nh, ce = (half + 1) * nh, col0 = chunk * g.NN;
+            const bool full = col0 + ce <= cols;
+            if (flip) {
+              if (full)
+                fwd_epilogue<true, true>(A0, A1, trow, cb, ce, col0, cols, wg, d);
+              else
+                fwd_epilogue<true, false>(A0, A1, trow, cb, ce, col0, cols, wg, d);
+            } else {
+              if (full)
+                fwd_epilogue<false, true>(A0, A1, trow, cb, ce, col0, cols, wg, d);
+              else
+                fwd_epilogue<false, false>(A0, A1, trow, cb, ce, col0, cols, wg, d);
             }
             tc_fence_before();
             __syncthreads();  // TMEM, As and wg may be overwritten now
