@@ -13,7 +13,7 @@ import threading
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnkfb200.so")
+_LIB_PATH = os.environ.get("NKFB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnkfb200.so")
 
 F32, F64 = 0, 1
 OP_NONE, OP_GATE, OP_ISING = 0, 1, 2
