@@ -8,6 +8,8 @@
 //   GEMM 2  G[i, f]     += X[s, i] Y[s, f]             UMMA 128 x NN x 16, A = the SAME X tile read MN-major
 //                                                      (rows = spins), B = Y MN-major; G stays in TMEM
 // and at the end G is read from TMEM and added to the fp64 accumulators with one atomic per element.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace nkfb {
@@ -58,8 +60,10 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t 
 // NB8: 8-column blocks of the chunk per thread (NN / 16).  The correction of the gate row, sum_s d_s w_eta
 // conj(rho_1) conj(tanh theta'), is accumulated per thread in 8 NB8 registers over ALL its sample tiles and reduced
 // over the 128 rows once at the end (a per-tile reduction costs 40 shuffles + 8 shared atomics per 8 columns).
-template <int NB8>
-__global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<float> psi, TcGradArgs a) {
+// NT threads: 256 (two column halves per sample row) or 512 (four quarters: sixteen warps hide the latencies of the
+// thread-per-row epilogue, which bounds this kernel, twice as well).
+template <int NB8, int NT>
+__global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi, TcGradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGeom g = a.g;
   const int NN = g.NN;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;
-  const int half = warp >> 2;
+  const int half = warp >> 2;  // column part of this warp (0 .. NT / 128 - 1)
   const uint32_t mbar_a = smem_u32(&mbar);
   const int chunk = blockIdx.x;
   const int N = g.N, M = g.M, cols = 2 * M;
@@ -96,15 +100,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
                                                        (size_t)chunk * g.b_chunk_bytes());
     uint4 *dst = reinterpret_cast<uint4 *>(Bs);
     const int n16 = (int)(g.b_chunk_bytes() / 16);
-    for (int i = tid; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
-    for (int n = tid; n < NN; n += TC_THREADS) {
+    for (int i = tid; i < n16; i += NT) dst[i] = __ldg(src + i);
+    for (int n = tid; n < NN; n += NT) {
       const int col = chunk * NN + n;
       wg[n] = (gate && col < cols) ? psi.W[(int64_t)gidx * cols + col] : 0.f;
       corr[n] = 0.f;
     }
     // rows >= KC*8 of the X tile (beyond the padded spin count) stay zero for the whole kernel
     uint4 *az = reinterpret_cast<uint4 *>(As);
-    for (int i = tid; i < GX_CHUNKS * TC_ROWS; i += TC_THREADS) az[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < GX_CHUNKS * TC_ROWS; i += NT) az[i] = make_uint4(0, 0, 0, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) infid_grad_tc_kernel(NetDev<flo
   const int64_t n_tiles = (a.S + TC_ROWS - 1) / TC_ROWS;
   const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
   const int64_t t_end = min(n_tiles, t_begin + a.tiles_per_split);
-  const int nh = NN / 2;
+  const int nh = NN / (NT / TC_ROWS);  // columns per part
   const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
   float ccacc[NB8][8];
 #pragma unroll
@@ -300,10 +304,16 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   if (N + 1 > TC_ROWS) return 1;  // GEMM 2 holds all gradient rows (spins + bias) in one UMMA M = 128 tile
   TcGeom g;
   // per column: three bf16 splits of a 128-sample Y tile (768 B) + gate row + correction (8 B)
-  if (!tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16)) return 1;
-  const size_t y_bytes = 3 * (size_t)(g.NN / 8) * TC_ROWS * 16;
-  const size_t smem = g.b_chunk_bytes() + (size_t)GX_CHUNKS * TC_ROWS * 16 + y_bytes + 2 * (size_t)g.NN * 4 +
-                      3 * TC_ROWS * sizeof(cx<float>) + 128;
+  auto smem_of = [](const TcGeom &q) {
+    return q.b_chunk_bytes() + (size_t)GX_CHUNKS * TC_ROWS * 16 + 3 * (size_t)(q.NN / 8) * TC_ROWS * 16 +
+           2 * (size_t)q.NN * 4 + 3 * TC_ROWS * sizeof(cx<float>) + 128;
+  };
+  // sixteen warps (chunks of a multiple of 32 columns, up to 128) when that geometry fits; else eight
+  bool wide = !getenv("NKFB_GRAD_TC_NARROW") &&
+              tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16, 226 * 1024, 32) &&
+              g.NN <= 128 && smem_of(g) <= (size_t)226 * 1024;
+  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16)) return 1;
+  const size_t smem = smem_of(g);
   if (smem > 227 * 1024) return 1;
 
   const size_t need = g.prep_bytes_per_net();
@@ -342,17 +352,23 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   a.tiles_per_split = (tiles + n_splits - 1) / n_splits;
   n_splits = (tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   dim3 grid(g.NC, (unsigned)n_splits);
-  const int nb8 = g.NN / 16;
-#define NKFB_GRAD_TC_CASE(NB)                                                                                     \
+#define NKFB_GRAD_TC_CASE(NB, NT)                                                                                 \
   case NB:                                                                                                       \
-    NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_grad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)smem));                                                         \
-    infid_grad_tc_kernel<NB><<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), a);                       \
+    NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_grad_tc_kernel<NB, NT>,                                         \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    infid_grad_tc_kernel<NB, NT><<<grid, NT, smem, st>>>(make_netdev<float>(psi), a);                           \
     break;
-  switch (nb8) {
-    NKFB_GRAD_TC_CASE(1) NKFB_GRAD_TC_CASE(2) NKFB_GRAD_TC_CASE(3) NKFB_GRAD_TC_CASE(4) NKFB_GRAD_TC_CASE(5)
-    NKFB_GRAD_TC_CASE(6) NKFB_GRAD_TC_CASE(7) NKFB_GRAD_TC_CASE(8)
-    default: return 1;  // wider chunks: CUDA-core kernel
+  if (wide) {
+    switch (g.NN / 32) {
+      NKFB_GRAD_TC_CASE(1, 512) NKFB_GRAD_TC_CASE(2, 512) NKFB_GRAD_TC_CASE(3, 512) NKFB_GRAD_TC_CASE(4, 512)
+      default: return 1;
+    }
+  } else {
+    switch (g.NN / 16) {
+      NKFB_GRAD_TC_CASE(1, 256) NKFB_GRAD_TC_CASE(2, 256) NKFB_GRAD_TC_CASE(3, 256) NKFB_GRAD_TC_CASE(4, 256)
+      NKFB_GRAD_TC_CASE(5, 256) NKFB_GRAD_TC_CASE(6, 256) NKFB_GRAD_TC_CASE(7, 256) NKFB_GRAD_TC_CASE(8, 256)
+      default: return 1;  // wider chunks: CUDA-core kernel
+    }
   }
 #undef NKFB_GRAD_TC_CASE
   NKFB_LAUNCHED(h);

@@ -25,7 +25,7 @@ struct TcGeom {
 // cols: real columns to cover; extra_col_bytes: additional shared memory per column (pass B keeps the three
 // bf16 splits of a 128-sample Y tile); x_bytes: bytes of the X tile
 inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_bytes = 0, size_t x_bytes = 0,
-                        size_t budget_bytes = 200 * 1024) {
+                        size_t budget_bytes = 200 * 1024, int nn_quantum = 16) {
   g->N = N;
   g->M = M;
   g->KT = ((N + 1 + 15) / 16) * 16;
@@ -36,10 +36,10 @@ inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_byte
   if (budget_bytes < x_bytes + 8192 + 4096) return false;
   const size_t budget = budget_bytes - x_bytes - 8192;
   int nn_max = (int)std::min<size_t>(256, budget / ((size_t)3 * g->KC * 16 + extra_col_bytes));
-  nn_max = (nn_max / 16) * 16;
-  if (nn_max < 16) return false;
+  nn_max = (nn_max / nn_quantum) * nn_quantum;
+  if (nn_max < nn_quantum) return false;
   g->NC = (cols + nn_max - 1) / nn_max;
-  g->NN = (((cols + g->NC - 1) / g->NC) + 15) / 16 * 16;
+  g->NN = (((cols + g->NC - 1) / g->NC) + nn_quantum - 1) / nn_quantum * nn_quantum;
   return g->KT <= 1024;
 }
 
@@ -196,6 +196,17 @@ __device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_
 #pragma unroll
     for (int w = 0; w < 4; ++w)
       if (live && w < W32) wd[w] = __ldg(packed + gs * W32 + w);
+    if (blockDim.x == 4 * TC_ROWS) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {  // 512 threads: kc = kc0 + 4 m, first spin 8 kc0 + 32 m: packed word m
+        const int kc = kc0 + 4 * m;
+        if (kc < g.KC) {
+          const int k0 = kc * 8;
+          emit(kc * TC_ROWS + r, k0, (wd[m] >> (k0 & 31)) & 0xFFu, live);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int m = 0; m < 8; ++m) {  // kc = kc0 + 2 m, first spin 8 kc0 + 16 m: packed word m / 2
       const int kc = kc0 + 2 * m;
@@ -206,7 +217,7 @@ __device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_
     }
     return;
   }
-  for (int idx = threadIdx.x; idx < g.KC * TC_ROWS; idx += TC_THREADS) {
+  for (int idx = threadIdx.x; idx < g.KC * TC_ROWS; idx += blockDim.x) {
     const int kc = idx / TC_ROWS, r = idx - kc * TC_ROWS;
     const int64_t gs = s_base + r;
     uint32_t bits = 0;

@@ -85,6 +85,79 @@ __global__ void k_dense(float *out, int iters) {
   if (r == 123.456f) out[0] = r;
 }
 
+
+// dense part with ND units per lane moved to the FP64 pipe: C chains x (NP pairs in packed FP32 + ND units in double)
+template <int C, int NP, int ND>
+__global__ void k_dense64(float *out, int iters) {
+  extern __shared__ float4 rows[];
+  double2 *drows = reinterpret_cast<double2 *>(rows + 2 * NP * 32);
+  for (int i = threadIdx.x; i < 2 * NP * 32; i += blockDim.x) rows[i] = make_float4(1.0001f, 0.9999f, 1e-4f, -1e-4f);
+  for (int i = threadIdx.x; i < 2 * ND * 32; i += blockDim.x) drows[i] = make_double2(1.0001, 1e-4);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  u64 zr[C][NP], zi[C][NP];
+  double dr[C][ND], di[C][ND];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { zr[c][p] = pk(0.1f + lane * 1e-3f, 0.2f); zi[c][p] = pk(0.05f, 0.01f * p); }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { dr[c][d] = 0.1 + lane * 1e-3; di[c][d] = 0.05 + 0.01 * d; }
+  }
+  const u64 one = pk(1.f, 1.f);
+  float acc = 0;
+  unsigned bit = lane & 1;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 *rp = rows + ((bit ^ c) & 1) * NP * 32 + lane;
+      const double2 *dp = drows + ((bit ^ c) & 1) * ND * 32 + lane;
+      u64 m[NP];
+      double md = 1.0;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const double2 q = dp[d * 32];
+        const double s = dr[c][d] * q.y, t = di[c][d] * q.y;
+        di[c][d] = fma(di[c][d], q.x, s);
+        dr[c][d] = fma(dr[c][d], q.x, -t);
+        double a = dr[c][d] + 1.0;
+        a = a * a;
+        a = fma(di[c][d], di[c][d], a);
+        md = d == 0 ? a : md * a;
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const float4 q = rp[p * 32];
+        const u64 ql = pk(q.x, q.y), qh = pk(q.z, q.w);
+        const u64 s = mul2(zr[c][p], qh), t = mul2(zi[c][p], qh);
+        zi[c][p] = fma2(zi[c][p], ql, s);
+        zr[c][p] = fma2(zr[c][p], ql, t ^ 0x8000000080000000ull);
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) { u64 a = add2(zr[c][p], one); a = mul2(a, a); m[p] = fma2(zi[c][p], zi[c][p], a); }
+      float lg = __log2f((float)md);
+#pragma unroll
+      for (int g = 0; g < NP; g += 4) {
+        u64 pr = m[g];
+#pragma unroll
+        for (int p = g + 1; p < g + 4 && p < NP; ++p) pr = mul2(pr, m[p]);
+        lg += __log2f(lo(pr) * hi(pr));
+      }
+      acc += lg;
+    }
+    bit ^= (it >> 3) & 1;
+  }
+  float r = acc;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) r += lo(zr[c][p]) + lo(zi[c][p]);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) r += (float)(dr[c][d] + di[c][d]);
+  }
+  if (r == 123.456f) out[0] = r;
+}
+
 template <typename F>
 float timeit(F f) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -115,5 +188,13 @@ int main() {
     printf("dense mode %d (0 full, 1 no LDS, 2 LDS only) C=%d NP=%d warps/SM %2d: %.0f cycles per warp-step, %.0f cycles per step-round/SMSP, %.1f chain-steps/kclk/SM\n", MODE, C, NP, w, cyc / 4000, cyc / 4000, \
            4000.0 * w * C / cyc * 1000); }
   RUN_DENSE(1, 7, 0) RUN_DENSE(1, 7, 1) RUN_DENSE(1, 7, 2) RUN_DENSE(2, 7, 0) RUN_DENSE(2, 7, 1) RUN_DENSE(2, 7, 2)
+#define RUN_D64(C, NP, ND) for (int w : {4, 8, 12, 16}) { \
+    const int sm = 2 * NP * 32 * 16 + 2 * ND * 32 * 16; \
+    cudaFuncSetAttribute(k_dense64<C, NP, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
+    float ms = timeit([&] { k_dense64<C, NP, ND><<<SM, w * 32, sm>>>(out, 4000); }); \
+    double cyc = ms * 1e-3 * ghz * 1e9; \
+    printf("dense64 C=%d: %d pairs FP32 + %d units FP64 per lane, warps/SM %2d: %.0f cycles per warp-step, %.1f chain-steps/kclk/SM\n", C, NP, ND, w, cyc / 4000, \
+           4000.0 * w * C / cyc * 1000); }
+  RUN_D64(1, 5, 3) RUN_D64(2, 5, 3) RUN_D64(2, 4, 5) RUN_D64(2, 5, 2) RUN_D64(2, 6, 1)
   return 0;
 }
