@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   const TcGeom g = a.g;
   unsigned char *Bs = smem;                             // 3 splits of the current chunk
   unsigned char *As = Bs + g.b_chunk_bytes();           // X tile
-  float *wg = reinterpret_cast<float *>(As + g.a_bytes());  // NN floats: row `idx` of W (this chunk) for the gate flip
+  uint4 *xtab = reinterpret_cast<uint4 *>(As + g.a_bytes());  // 256 x 16 B: bf16 images of 8 spins (tc_build_x_tile)
+  float *wg = reinterpret_cast<float *>(xtab + 256);        // NN floats: row `idx` of W (this chunk) for the gate flip
   cx<float> *xch = reinterpret_cast<cx<float> *>(wg + g.NN);  // exchange buffer [7][TC_ROWS]
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_sh;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), 256);
+  tc_fill_x_table(xtab, a.s0, a.s1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
                 wg[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
               }
             }
-            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1);
+            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, false, xtab);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -350,10 +352,11 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   // log-cosh epilogue; the W~ chunk of a CTA is sized for half of the shared memory
   size_t budget = 104 * 1024;
   if (const char *e = getenv("NKFB_TC_FWD_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
-  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, 0, budget) &&
-      !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden))
+  const size_t xb = (size_t)(((psi->n_visible + 1 + 15) / 16) * 2) * TC_ROWS * 16 + 4096;  // X tile + spin-group table
+  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb, budget) &&
+      !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb))
     return 1;
-  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + (size_t)g.NN * 4 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
+  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 4 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
   if (smem > 227 * 1024) return 1;
 
   // prepared bf16 splits of both networks live in the handle's second workspace

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
   unsigned char *Bs = smem;                                      // W~ chunk, 3 splits, resident
   unsigned char *As = Bs + g.b_chunk_bytes();                    // X tile [16][128][8] bf16
   unsigned char *Ys = As + (size_t)GX_CHUNKS * TC_ROWS * 16;     // Y tile, 3 splits of [NN/8][128][8] bf16
-  float *wg = reinterpret_cast<float *>(Ys + 3 * y_split_bytes);  // NN: row idx of W (gate flip)
+  uint4 *xtab = reinterpret_cast<uint4 *>(Ys + 3 * y_split_bytes);  // 256 x 16 B: bf16 images of 8 spins
+  float *wg = reinterpret_cast<float *>(xtab + 256);               // NN: row idx of W (gate flip)
   float *corr = wg + NN;                                         // NN: correction of row idx
   cx<float> *wts = reinterpret_cast<cx<float> *>(corr + NN);     // [3][128]: w_sig, w_eta, conj(rho1)
   __shared__ __align__(8) uint64_t mbar;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
     // rows >= KC*8 of the X tile (beyond the padded spin count) stay zero for the whole kernel
     uint4 *az = reinterpret_cast<uint4 *>(As);
     for (int i = tid; i < GX_CHUNKS * TC_ROWS; i += NT) az[i] = make_uint4(0, 0, 0, 0);
+    tc_fill_x_table(xtab, a.s0, a.s1);
   }
   tc_fence_before();
   __syncthreads();
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
     for (int side = 0; side < 2; ++side) {
       const uint32_t *packed = side == 0 ? a.sigma : a.eta;
       const bool flip = gate && side == 1;
-      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, true);
+      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, true, xtab);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -305,14 +307,14 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   TcGeom g;
   // per column: three bf16 splits of a 128-sample Y tile (768 B) + gate row + correction (8 B)
   auto smem_of = [](const TcGeom &q) {
-    return q.b_chunk_bytes() + (size_t)GX_CHUNKS * TC_ROWS * 16 + 3 * (size_t)(q.NN / 8) * TC_ROWS * 16 +
+    return q.b_chunk_bytes() + (size_t)GX_CHUNKS * TC_ROWS * 16 + 3 * (size_t)(q.NN / 8) * TC_ROWS * 16 + 4096 +
            2 * (size_t)q.NN * 4 + 3 * TC_ROWS * sizeof(cx<float>) + 128;
   };
   // sixteen warps (chunks of a multiple of 32 columns, up to 128) when that geometry fits; else eight
   bool wide = !getenv("NKFB_GRAD_TC_NARROW") &&
-              tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16, 226 * 1024, 32) &&
+              tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16 + 4096, 226 * 1024, 32) &&
               g.NN <= 128 && smem_of(g) <= (size_t)226 * 1024;
-  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16)) return 1;
+  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, (size_t)GX_CHUNKS * TC_ROWS * 16 + 4096)) return 1;
   const size_t smem = smem_of(g);
   if (smem > 227 * 1024) return 1;
 

@@ -170,11 +170,30 @@ static __global__ void tc_prep_kernel(NetDev<float> net, TcGeom g, __nv_bfloat16
 // trips per tile at C4, 13 % of the estimator's time on the long scoreboard) and cuts the groups out of registers.
 // (single_load = false keeps the per-group loads: with two CTAs per SM the estimator hides that latency and the
 // shorter code wins there -- measured.)
+// xtab (optional, shared memory, tc_fill_x_table): the 16 bytes of every group of 8 spins, indexed by its 8 bits --
+// one LDS.128 instead of eight shift / test / select rounds for the groups that lie entirely below N (the bit
+// arithmetic was a fifth of the instructions of the tensor-core kernels).
+__device__ __forceinline__ void tc_fill_x_table(uint4 *xtab, float s0, float s1) {
+  const uint32_t b0 = __bfloat16_as_ushort(__float2bfloat16_rn(s0)), b1 = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      w[q] = (((b >> (2 * q)) & 1) ? b1 : b0) | ((((b >> (2 * q + 1)) & 1) ? b1 : b0) << 16);
+    xtab[b] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 __device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_t *packed, int64_t s_base, int64_t S,
-                                                const TcGeom &g, float s0, float s1, bool single_load = false) {
+                                                const TcGeom &g, float s0, float s1, bool single_load = false,
+                                                const uint4 *xtab = nullptr) {
   const int W32 = (g.N + 31) >> 5;
   const uint16_t b0 = __bfloat16_as_ushort(__float2bfloat16_rn(s0)), b1 = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
   auto emit = [&](int idx, int k0, uint32_t bits, bool live) {
+    if (xtab != nullptr && k0 + 8 <= g.N) {
+      *reinterpret_cast<uint4 *>(As + (size_t)idx * 16) = live ? xtab[bits] : make_uint4(0, 0, 0, 0);
+      return;
+    }
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
