@@ -342,7 +342,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "kernel": "sample_ratio_cta_kernel", "achieved": achieved / 1e9,
                          "peak": peak / 1e9, "unit": "G hidden-unit updates/s", "frac": achieved / peak,
-                         "traffic": 1451776,
+                         "traffic": 1209344,
                          "note": (f"the dominant kernel is bound by the FP32 pipe, neither HBM nor tensor: algorithmic work = "
                                   f"{evals_per_launch:.3e} hidden-unit updates per launch (chains x sweeps x N x M) at "
                                   f"{ops_per_eval:.0f} FP32-pipe operations each (complex multiply, |1+z|^2, product; no "
@@ -354,8 +354,8 @@ def run_b200(args):
                          "hbm_view": {"bound": "hbm", "achieved": bytes_per_launch / t_launch / 1e9, "peak": hbm_gbs,
                                       "unit": "GB/s", "frac": bytes_per_launch / t_launch / 1e9 / hbm_gbs,
                                       "peak_source": how},
-                         "traffic_note": "dram__bytes_read+write of one sampler launch from profiles/r01_ncu_top_kernels.md "
-                                         "(1.45 MB read + 256 B written: tables and packed samples stay in L2)",
+                         "traffic_note": "dram__bytes_read+write of one sampler launch from profiles/r01_ncu_top_kernels_v3.md "
+                                         "(1.21 MB read, 0 B written: tables and packed samples stay in L2)",
                          "other_kernels": other},
             "result": {"infidelity": infid, "acceptance": acc_rate},
             **({"cuda_graph": {"ms_per_step": graph_ms, "value": S_total / (graph_ms * 1e-3), "unit": UNIT,
