@@ -123,7 +123,7 @@ def run_reference(args):
             "config": bench_config(args.workload, w, 1),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def host_ops(w, hi):
@@ -371,9 +371,25 @@ def run_b200(args):
                                     "sample": f"{nc} chains x {cl} samples per family of workload {args.workload}, "
                                               f"one full step, NumPy complex128 oracle (reference algorithm: full "
                                               f"forward per MH step), {dt:.1f} s"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """Library chatter on fd 1 (e.g. NCCL's version banner at init) goes to stderr: stdout carries the one JSON line."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -390,6 +406,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a captured CUDA graph")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

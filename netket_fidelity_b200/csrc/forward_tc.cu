@@ -26,10 +26,9 @@ struct LcAcc {
   // log cosh z = |x| + log((1 + t e^{-2iy}) / 2) (folded): multiply the running product by (1 + t e^{-2iy}) / 2,
   // which is ~1 for small theta, so that the log taken every 8 units is small and keeps its absolute accuracy
   __device__ __forceinline__ void add(float x, float y, float &pr, float &pi) {
-    if (x < 0.f) {
-      x = -x;
-      y = -y;
-    }
+    // fold theta to Re >= 0: (x, y) -> (|x|, y sgn x), the sign bit of x moved onto y with one logic operation
+    y = __uint_as_float(__float_as_uint(y) ^ (__float_as_uint(x) & 0x80000000u));
+    x = fabsf(x);
     const float t = mufu_ex2(x * (float)(-2.0 * LOG2E));
     const float a = 2.f * y;
     float c, s;
@@ -114,6 +113,7 @@ struct TcFwdArgs {
   const __nv_bfloat16 *prep_psi, *prep_phi;
   TcGeom g;
   int64_t n_groups;
+  int single_load;  // X tile: one packed-row load per thread (tc_build_x_tile)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
                 wg[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
               }
             }
-            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, false, xtab);
+            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, a.single_load != 0, xtab);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -398,6 +398,7 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   a.g = g;
   const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
   a.n_groups = (tiles + TC_T - 1) / TC_T;
+  a.single_load = getenv("NKFB_TC_FWD_SINGLE") ? 1 : 0;
   NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem <= 112 * 1024 ? 2 : 1;
   const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);

@@ -32,18 +32,14 @@ struct TcGradArgs {
 };
 
 // tanh z with MUFU: sg ((1 - t^2) + 2 i t sin 2y) / (1 + 2 t cos 2y + t^2), t = e^{-2|x|}
+// (tanh is odd and the imaginary part 2 t sin 2y / den is even in the fold (x, y) -> (-x, -y), so only the sign of
+// the real part has to follow x: no selects)
 __device__ __forceinline__ cx<float> ctanh_fast(float x, float y) {
-  float sg = 1.f;
-  if (x < 0.f) {
-    x = -x;
-    y = -y;
-    sg = -1.f;
-  }
-  const float t = mufu_ex2(x * (float)(-2.0 * LOG2E));
+  const float t = mufu_ex2(fabsf(x) * (float)(-2.0 * LOG2E));
   const float a = 2.f * y;
   const float c = mufu_cos(a), s = mufu_sin(a);
-  const float inv = __fdividef(sg, fmaf(t, fmaf(2.f, c, t), 1.f));
-  return mk<float>((1.f - t * t) * inv, 2.f * t * s * inv);
+  const float inv = __fdividef(1.f, fmaf(t, fmaf(2.f, c, t), 1.f));
+  return mk<float>(copysignf((1.f - t * t) * inv, x), 2.f * t * s * inv);
 }
 
 __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
