@@ -1054,7 +1054,8 @@ static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampAr
                             const int *site_seq, const R *a0_seq, cudaStream_t st) {
   int W, TSH;
   ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
-  if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning override
+  if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning overrides
+  if (const char *e = getenv("NKFB_CTA_TSH")) TSH = atoi(e);
   const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH, (net->n_visible + 31) >> 5);
   cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
