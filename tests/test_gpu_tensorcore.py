@@ -58,3 +58,30 @@ def test_tc_estimator_and_gradient(h, N, M, S, std, cv):
         os.environ.pop("NKFB_GRAD_IMPL")
         # the two implementations must also agree with each other on the per-sample estimator
         assert rel_err(out["tc"][0], out["simt"][0]) <= 1e-4
+
+
+@pytest.mark.parametrize("N,M,S,std", [(100, 400, 4096, 0.01), (20, 200, 2100, 0.05), (37, 90, 2500, 0.05)])
+def test_tc_gradient_eight_and_sixteen_warp_forms_agree(h, monkeypatch, N, M, S, std):
+    """Pass B on tensor cores has two forms: sixteen warps (four column quarters per sample row, chunks of a multiple
+    of 32 columns, the default where that geometry fits) and eight warps (two halves).  Same tiles, same arithmetic
+    per element: the gradients agree to the rounding of the fp64 atomics, and both with the oracle.  (20, 200) has no
+    sixteen-warp geometry (224-column chunks): both calls take the eight-warp form there."""
+    rng = np.random.default_rng(11)
+    psi, phi = _net(N, M, 1234, std), _net(N, M, 5678, std)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    a, b = to_rbmspec(psi, torch.complex64), to_rbmspec(phi, torch.complex64)
+    U, Ud = oops.Rx(N, N - 1, 0.37), oops.Rx(N, N - 1, -0.37)
+    U1, U2, U4 = mode_slots("upsi", U, Ud)
+    ref = infidelity_and_grad(psi, phi, sigma, eta, -0.5, U1, U2, U4)
+    monkeypatch.setenv("NKFB_FWD_IMPL", "tc")
+    monkeypatch.setenv("NKFB_GRAD_IMPL", "tc")
+    lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, -0.5, to_opspec(U1), to_opspec(U2), to_opspec(U4))
+    g = {}
+    for form in ("wide", "narrow"):
+        if form == "narrow":
+            monkeypatch.setenv("NKFB_GRAD_TC_NARROW", "1")
+        gacc = h.infidelity_grad(a, sp, ep, LS, -0.5, lv, rho1, sums, to_opspec(U2))
+        g[form] = h.grad_finalize(gacc, sums, a.n_params, torch.complex64).cpu().numpy()
+        assert rel_err(g[form], ref["grad"].ravel()) <= 2e-4, (form, rel_err(g[form], ref["grad"].ravel()))
+    assert rel_err(g["wide"], g["narrow"]) <= 1e-6, rel_err(g["wide"], g["narrow"])
