@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   unsigned char *Bs = smem;                             // 3 splits of the current chunk
   unsigned char *As = Bs + g.b_chunk_bytes();           // X tile
   uint4 *xtab = reinterpret_cast<uint4 *>(As + g.a_bytes());  // 256 x 16 B: bf16 images of 8 spins (tc_build_x_tile)
-  float *wg = reinterpret_cast<float *>(xtab + 256);        // NN floats: row `idx` of W (this chunk) for the gate flip
-  cx<float> *xch = reinterpret_cast<cx<float> *>(wg + g.NN);  // exchange buffer [7][TC_ROWS]
+  float *wg = reinterpret_cast<float *>(xtab + 256);        // [2][NN] floats: row `idx` of W (this chunk) for the gate flip
+  cx<float> *xch = reinterpret_cast<cx<float> *>(wg + 2 * g.NN);  // exchange buffer [7][TC_ROWS]
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_sh;
   __shared__ double red[8];
@@ -176,68 +176,85 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
           const int n16 = (int)(g.b_chunk_bytes() / 16);
           for (int i = tid; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
         }
-#pragma unroll
-        for (int t = 0; t < TC_T; ++t) {
-#pragma unroll
-          for (int side = 0; side < 2; ++side) {
-            const int ev = netid * 2 + side;
-            const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
-            const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
-            const uint32_t *packed = side == 0 ? a.sigma : a.eta;
-            const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
-            if (flip) {
-              for (int n = tid; n < g.NN; n += TC_THREADS) {
-                const int col = chunk * g.NN + n;
-                wg[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
-              }
+        // The 2 TC_T phases (tile, side) of this chunk, software-pipelined when two accumulators fit the CTA's 256
+        // TMEM columns: the X tile and the UMMAs of phase p + 1 are issued BEFORE the epilogue of phase p (the X
+        // buffer is free as soon as the UMMAs of phase p have completed), so the tensor pipe works under the
+        // epilogue instead of in front of it.
+        const bool dbuf = 2 * g.NN <= 256;
+        auto issue = [&](int p) {
+          const int t = p >> 1, side = p & 1;
+          const int ev = netid * 2 + side;
+          const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+          const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
+          const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+          const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+          if (flip) {
+            float *wgp = wg + (p & 1) * g.NN;
+            for (int n = tid; n < g.NN; n += TC_THREADS) {
+              const int col = chunk * g.NN + n;
+              wgp[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
             }
-            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, a.single_load != 0, xtab);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-              tc_fence_after();
-              const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
-              for (int s = 0; s < 3; ++s)
-                for (int ks = 0; ks < g.KS; ++ks) {
-                  const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
-                  const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (g.NN * 16),
-                                                g.NN * 16, 128);
-                  umma_bf16(tmem_d, ad, bd, idesc, (s | ks) ? 1u : 0u);
-                }
-              umma_commit(mbar_a);
-            }
-            mbar_wait(mbar_a, parity);
-            parity ^= 1;
-            tc_fence_after();
-            // ---- epilogue: this thread's row, its half of the chunk's columns
-            float d = 0.f;
-            if (flip) {
-              const int64_t gs = s_base + row;
-              if (gs < a.S) {
-                const uint32_t w = packed[gs * W32 + (op.idx >> 5)];
-                d = ssum - 2.f * (((w >> (op.idx & 31)) & 1u) ? a.s1 : a.s0);
-              }
-            }
-            LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
-            const int nh = g.NN / 2;  // columns per half (multiple of 8)
-            const uint32_t trow = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16);
-            const int cb = half * nh, ce = (half + 1) * nh, col0 = chunk * g.NN;
-            const bool full = col0 + ce <= cols;
-            if (flip) {
-              if (full)
-                fwd_epilogue<true, true>(A0, A1, trow, cb, ce, col0, cols, wg, d);
-              else
-                fwd_epilogue<true, false>(A0, A1, trow, cb, ce, col0, cols, wg, d);
-            } else {
-              if (full)
-                fwd_epilogue<false, true>(A0, A1, trow, cb, ce, col0, cols, wg, d);
-              else
-                fwd_epilogue<false, false>(A0, A1, trow, cb, ce, col0, cols, wg, d);
-            }
-            tc_fence_before();
-            __syncthreads();  // TMEM, As and wg may be overwritten now
           }
+          tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, a.single_load != 0, xtab);
+          fence_async_smem();
+          tc_fence_before();
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+            const uint32_t td = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u);
+            for (int s = 0; s < 3; ++s)
+              for (int ks = 0; ks < g.KS; ++ks) {
+                const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (g.NN * 16),
+                                              g.NN * 16, 128);
+                umma_bf16(td, ad, bd, idesc, (s | ks) ? 1u : 0u);
+              }
+            umma_commit(mbar_a);
+          }
+        };
+        if (dbuf) issue(0);
+#pragma unroll
+        for (int p = 0; p < 2 * TC_T; ++p) {
+          const int t = p >> 1, side = p & 1;
+          const int ev = netid * 2 + side;
+          const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+          const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
+          const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+          const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+          if (!dbuf) issue(p);
+          mbar_wait(mbar_a, parity);
+          parity ^= 1;
+          tc_fence_after();
+          if (dbuf && p + 1 < 2 * TC_T) issue(p + 1);
+          // ---- epilogue: this thread's row, its half of the chunk's columns
+          float d = 0.f;
+          if (flip) {
+            const int64_t gs = s_base + row;
+            if (gs < a.S) {
+              const uint32_t w = packed[gs * W32 + (op.idx >> 5)];
+              d = ssum - 2.f * (((w >> (op.idx & 31)) & 1u) ? a.s1 : a.s0);
+            }
+          }
+          LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
+          const int nh = g.NN / 2;  // columns per half (multiple of 8)
+          const uint32_t trow = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u) + ((uint32_t)(32 * (warp & 3)) << 16);
+          const float *wgp = wg + (p & 1) * g.NN;
+          const int cb = half * nh, ce = (half + 1) * nh, col0 = chunk * g.NN;
+          const bool full = col0 + ce <= cols;
+          if (flip) {
+            if (full)
+              fwd_epilogue<true, true>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
+            else
+              fwd_epilogue<true, false>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
+          } else {
+            if (full)
+              fwd_epilogue<false, true>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
+            else
+              fwd_epilogue<false, false>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
+          }
+          tc_fence_before();
+          __syncthreads();  // this phase's TMEM buffer and gate row may be overwritten now
         }
       }
     }
@@ -356,7 +373,7 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb, budget) &&
       !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb))
     return 1;
-  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 4 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
+  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 8 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
   if (smem > 227 * 1024) return 1;
 
   // prepared bf16 splits of both networks live in the handle's second workspace
