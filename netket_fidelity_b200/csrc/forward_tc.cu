@@ -114,6 +114,7 @@ struct TcFwdArgs {
   TcGeom g;
   int64_t n_groups;
   int single_load;  // X tile: one packed-row load per thread (tc_build_x_tile)
+  int tmem_cols;    // TMEM columns this CTA allocates
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
     mbar_init(mbar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), 256);
+  // 256 columns per CTA (two CTAs share the SM's 512); all 512 when the CTA is alone on its SM (a.tmem_cols)
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), a.tmem_cols);
   tc_fill_x_table(xtab, a.s0, a.s1);
   tc_fence_before();
   __syncthreads();
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
         // TMEM columns: the X tile and the UMMAs of phase p + 1 are issued BEFORE the epilogue of phase p (the X
         // buffer is free as soon as the UMMAs of phase p have completed), so the tensor pipe works under the
         // epilogue instead of in front of it.
-        const bool dbuf = 2 * g.NN <= 256;
+        const bool dbuf = 2 * g.NN <= a.tmem_cols;
         auto issue = [&](int p) {
           const int t = p >> 1, side = p & 1;
           const int ev = netid * 2 + side;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 256);
+  if (warp == 0) tmem_dealloc(tmem_d, a.tmem_cols);
 }
 
 // returns NKFB_OK, an error, or 1 when the tensor-core path does not apply (caller falls back to the SIMT kernel)
@@ -416,6 +418,7 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
   a.n_groups = (tiles + TC_T - 1) / TC_T;
   a.single_load = getenv("NKFB_TC_FWD_SINGLE") ? 1 : 0;
+  a.tmem_cols = smem > (size_t)115 * 1024 ? 512 : 256;  // more than half of the SM's shared memory: one CTA per SM
   NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem <= 112 * 1024 ? 2 : 1;
   const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);
