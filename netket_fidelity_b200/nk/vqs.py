@@ -298,7 +298,14 @@ class MCState(_RBMStateBase):
         cols = S // rows
         l_block = max(1, cols // 32)
         n_blocks = cols // l_block
-        part = self._h.chain_stats(L, rows, cols, l_block, n_blocks).cpu().numpy()
+        part = self._h.chain_stats(L, rows, cols, l_block, n_blocks)
+        if self._world > 1 and sums is not None:
+            # chain / block partial sums of every rank (rows x (3 + n_blocks) doubles each): the statistics below
+            # are those of all chains of the job, not of this rank's shard
+            from ..parallel import allgather_rows
+            part = allgather_rows(part)
+            rows = rows * self._world
+        part = part.cpu().numpy()
         tot, tot2 = float(part[:, 0].sum()), None
         if sums is not None:
             s = sums.cpu().numpy() if torch.is_tensor(sums) else np.asarray(sums)

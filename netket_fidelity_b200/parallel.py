@@ -39,6 +39,18 @@ def allreduce_sum_(t: torch.Tensor, group=None):
     return t
 
 
+def allgather_rows(t: torch.Tensor, group=None):
+    """Concatenates the equally shaped (rows_local, k) tensors of all ranks along dim 0, in rank order -- the
+    per-chain partial sums of nk.stats (chain c of rank r is global chain r * rows_local + c), so that
+    error_of_mean / tau_corr / R_hat are those of ALL chains, as NetKet's mpi_statistics computes them."""
+    world, _ = world_info(group)
+    if world == 1:
+        return t
+    out = [torch.empty_like(t) for _ in range(world)]
+    torch.distributed.all_gather(out, t.contiguous(), group=group)
+    return torch.cat(out, dim=0)
+
+
 def finalize_mean_var(sums):
     """sums = [sum L, sum L^2, ., ., n, ...] (global) -> (F, variance)."""
     n = float(sums[4])

@@ -83,6 +83,54 @@ def test_two_rank_allreduce_reproduces_single_rank_result():
     assert res == [(0, True), (1, True)]
 
 
+def _partials(x, l_block, n_blocks):
+    """NumPy restatement of nkfb_chain_stats: per row [sum, sum of the first half, sum of the second half, block sums]."""
+    rows, cols = x.shape
+    half = cols // 2
+    blk = x[:, :l_block * n_blocks].reshape(rows, n_blocks, l_block).sum(-1)
+    return np.concatenate([x.sum(1, keepdims=True), x[:, :half].sum(1, keepdims=True),
+                           x[:, half:2 * half].sum(1, keepdims=True), blk], axis=1)
+
+
+def _stats_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from netket_fidelity_b200 import parallel as par
+    from netket_fidelity_b200.nk.stats import stats_from_partials
+    rows_local, cols, l_block = 24, 64, 2
+    n_blocks = cols // l_block
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(world * rows_local, cols)).cumsum(1) * 0.1 + rng.normal(size=(world * rows_local, 1))
+    mine = x[rank * rows_local:(rank + 1) * rows_local]
+    part = par.allgather_rows(torch.tensor(_partials(mine, l_block, n_blocks)))
+    sums = torch.tensor([mine.sum(), (mine ** 2).sum(), 0, 0, mine.size, 0, 0, 0], dtype=torch.float64)
+    par.allreduce_sum_(sums)
+    mean, var = par.finalize_mean_var(sums)
+    rows = rows_local * world
+    st = stats_from_partials(part.numpy(), rows, cols, l_block, n_blocks, var * rows * cols)
+    ref = stats_from_partials(_partials(x, l_block, n_blocks), rows, cols, l_block, n_blocks, ((x - x.mean()) ** 2).sum())
+    ok = (part.shape == (rows, 3 + n_blocks) and abs(st.error_of_mean - ref.error_of_mean) < 1e-12
+          and abs(st.R_hat - ref.R_hat) < 1e-12 and abs(st.tau_corr - ref.tau_corr) < 1e-9
+          and abs(mean - x.mean()) < 1e-12 and abs(var - x.var()) < 1e-12 and st.R_hat > 1.0)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_chain_statistics_are_those_of_all_chains():
+    """error_of_mean / tau_corr / R_hat with G > 1: the per-chain partial sums of every rank are all-gathered
+    (parallel.allgather_rows), so the statistics equal those of one process holding all chains."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
 def test_shard_chains_errors():
     from netket_fidelity_b200 import parallel as par
     assert par.shard_chains(16, 4, 3) == (12, 4)
