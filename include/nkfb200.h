@@ -174,7 +174,10 @@ int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t
  *   acc_k += sum_s [ w_sig conj O_k(sigma_s) + w_eta conj D_k(eta_s) ],
  *   w_eta = conj A + 2 cv |A|^2,  w_sig = 2 (L_s - F) - w_eta,  F = sums[0]/sums[4]
  * (sums must already hold the GLOBAL sums, i.e. after the scalar all-reduce).
- * grad_acc: device double[2*(M + N*M + N)], complex128 accumulators in the flat layout. */
+ * grad_acc: device double[2*(M + N*M + N)], complex128 accumulators in the flat layout.
+ * op2 of kind NKFB_OP_ISING ((N+1)-connected U^dagger acting on psi): D_k is evaluated on the explicit
+ * batch of connected configurations in handle-owned scratch (<= 256 MiB, grown on first use; do not
+ * capture that first call in a CUDA graph); rho1 is not read. */
 int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2,
                          const uint32_t *sigma, const uint32_t *eta, int64_t S,
                          const double local_states[2], double cv_coeff,

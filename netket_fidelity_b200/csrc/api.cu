@@ -208,6 +208,7 @@ extern "C" int nkfb_destroy(nkfb_handle_t h) {
   if (h->ws) cudaFree(h->ws);
   if (h->ws2) cudaFree(h->ws2);
   if (h->ws3) cudaFree(h->ws3);
+  if (h->ws4) cudaFree(h->ws4);
   delete h;
   return NKFB_OK;
 }

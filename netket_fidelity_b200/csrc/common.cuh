@@ -18,6 +18,8 @@ struct nkfb_handle_s {
   size_t ws2_bytes;
   void *ws3;       // scratch: bf16 splits of the RBM kernel for the tensor-core gradient
   size_t ws3_bytes;
+  void *ws4;       // scratch: connected batch (packed rows, log-amplitudes, weights) of the Ising-type U^dagger gradient
+  size_t ws4_bytes;
   int opt_sampler_algo;  // NKFB_OPT_SAMPLER_ALGO
 };
 

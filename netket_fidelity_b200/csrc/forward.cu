@@ -497,6 +497,126 @@ static int launch_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   return NKFB_OK;
 }
 
+// ------------------------------------------------------------------ gradient with an Ising-type U^dagger
+// (is_unitary=True with an (N+1)-connected operator acting on psi; reference overlap_U/expect.py:101-120 with
+// U_dagger an IsingJax-like DiscreteJaxOperator).  The eta term of the gradient is
+//   sum_s w_eta[s] sum_c conj(rho_{s,c}) conj(O_k(eta'_{s,c})),  rho_{s,c} = mel_c psi(eta'_{s,c}) / sum_c' (...)
+// and is evaluated on the explicit batch of the (N+1) S connected configurations: bit-packed expansion ->
+// logpsi kernel -> per-sample log-sum-exp weights -> the weighted-score form of the gradient kernel.
+__global__ void expand_flips_kernel(const uint32_t *eta, int64_t S, int N, uint32_t *out) {
+  const int W32 = (N + 31) >> 5, C = N + 1;
+  const int64_t total = S * C * W32;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / W32;
+    const int w = (int)(idx - row * W32);
+    const int64_t s = row / C;
+    const int c = (int)(row - s * C);
+    uint32_t word = eta[s * W32 + w];
+    if (c > 0 && ((c - 1) >> 5) == w) word ^= 1u << ((c - 1) & 31);
+    out[idx] = word;
+  }
+}
+
+// one warp per sample: rho_c from the log-amplitudes of the connected configurations and the matrix elements of
+// the operator, then w_sig[s] and w_exp[s, c] = w_eta[s] conj(rho_{s,c})  (same weights as infid_grad_kernel)
+template <typename R>
+__global__ void ising_weights_kernel(OpDev op, const uint32_t *eta, int64_t S, int N, const cx<R> *lp,
+                                     const cx<R> *log_val, const double *sums, R cvc, cx<R> *w_sig,
+                                     cx<R> *w_exp) {
+  const int W32 = (N + 31) >> 5, C = N + 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double F = sums[0] / sums[4];
+  for (int64_t s = warp0; s < S; s += nwarps) {
+    const cx<R> *am = lp + s * C;
+    const uint32_t *x = eta + s * W32;
+    R mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmax(mx, am[c].re);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    R zz = R(0);
+    for (int e = lane; e < op.n_edges; e += 32) {
+      const int ia = op.edges[2 * e], ib = op.edges[2 * e + 1];
+      const uint32_t ba = (x[ia >> 5] >> (ia & 31)) & 1u, bb = (x[ib >> 5] >> (ib & 31)) & 1u;
+      zz += (ba == bb) ? R(1) : R(-1);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) zz += __shfl_xor_sync(0xffffffffu, zz, m);
+    const cx<R> mdiag = mk<R>((R)op.c0[0] + (R)op.c1[0] * zz, (R)op.c0[1] + (R)op.c1[1] * zz);
+    const cx<R> moff = mk<R>((R)op.c2[0], (R)op.c2[1]);
+    cx<R> sum = mk<R>(0, 0);
+    for (int c = lane; c < C; c += 32)
+      sum = sum + (c == 0 ? mdiag : moff) * cexp(mk<R>(am[c].re - mx, am[c].im));
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      sum.re += __shfl_xor_sync(0xffffffffu, sum.re, m);
+      sum.im += __shfl_xor_sync(0xffffffffu, sum.im, m);
+    }
+    const cx<R> A = cexp(log_val[s]);
+    const R A2 = abs2(A);
+    const R Lv = A.re + cvc * (A2 - R(1));
+    const cx<R> we = mk<R>(A.re + R(2) * cvc * A2, -A.im);
+    if (lane == 0) {
+      const R dl = (R)(2.0 * ((double)Lv - F));
+      w_sig[s] = mk<R>(dl - we.re, -we.im);
+    }
+    const R inv = R(1) / abs2(sum);
+    for (int c = lane; c < C; c += 32) {
+      const cx<R> e = (c == 0 ? mdiag : moff) * cexp(mk<R>(am[c].re - mx, am[c].im));
+      const cx<R> rho = inv * (e * conj(sum));
+      w_exp[s * C + c] = we * conj(rho);
+    }
+  }
+}
+
+template <typename R, int SPT>
+static int launch_grad_ising(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
+                             const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
+                             const double *sums, double *grad_acc, cudaStream_t st) {
+  const int N = psi->n_visible, C = N + 1, W32 = (N + 31) >> 5;
+  // scratch per sample: C packed rows, C log-amplitudes, C + 1 weights; chunks of at most ~256 MiB
+  const size_t per_sample = (size_t)C * (W32 * 4 + 2 * sizeof(cx<R>)) + sizeof(cx<R>);
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(S, (int64_t)((size_t(256) << 20) / per_sample)));
+  const size_t need = per_sample * (size_t)chunk + 64;
+  if (h->ws4_bytes < need) {
+    if (h->ws4) cudaFree(h->ws4);
+    h->ws4 = nullptr;
+    h->ws4_bytes = 0;
+    NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws4, need));
+    h->ws4_bytes = need;
+  }
+  // 16-byte aligned carve-up: complex arrays first
+  cx<R> *lp = reinterpret_cast<cx<R> *>(h->ws4);
+  cx<R> *w_exp = lp + (size_t)chunk * C;
+  cx<R> *w_sig = w_exp + (size_t)chunk * C;
+  uint32_t *xp = reinterpret_cast<uint32_t *>(w_sig + chunk);
+  const bool has_cv = !isnan(cv);
+  const OpDev od = make_opdev(op2);
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t n = std::min<int64_t>(chunk, S - s0);
+    const uint32_t *eta_c = eta + s0 * W32, *sig_c = sigma + s0 * W32;
+    const int64_t B = n * C;
+    int grid = (int)std::min<int64_t>((B * W32 + 255) / 256, (int64_t)h->sm_count * 16);
+    expand_flips_kernel<<<grid, 256, 0, st>>>(eta_c, n, N, xp);
+    NKFB_LAUNCHED(h);
+    int rc = launch_logpsi<R, SPT>(h, psi, nullptr, xp, B, ls, lp, st);
+    if (rc) return rc;
+    grid = (int)std::min<int64_t>((n * 32 + 255) / 256, (int64_t)h->sm_count * 16);
+    ising_weights_kernel<R><<<grid, 256, 0, st>>>(od, eta_c, n, N, lp,
+                                                  reinterpret_cast<const cx<R> *>(log_val) + s0, sums,
+                                                  has_cv ? (R)cv : R(0), w_sig, w_exp);
+    NKFB_LAUNCHED(h);
+    rc = launch_grad<R, SPT>(h, psi, nullptr, sig_c, sig_c, n, ls, NAN, nullptr, nullptr, nullptr, grad_acc, st,
+                             w_sig);
+    if (rc) return rc;
+    rc = launch_grad<R, SPT>(h, psi, nullptr, xp, xp, B, ls, NAN, nullptr, nullptr, nullptr, grad_acc, st, w_exp);
+    if (rc) return rc;
+  }
+  return NKFB_OK;
+}
+
 }  // namespace nkfb
 
 using namespace nkfb;
@@ -574,13 +694,17 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
   if (rc) return rc;
   rc = check_op(h, op2, psi->n_visible);
   if (rc) return rc;
-  if (op2 && op2->kind == NKFB_OP_ISING)
-    NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED,
-              "gradient with an Ising-type U^dagger acting on psi (is_unitary=True with Ising) is not implemented; "
-              "use sample_Upsi=True");
   if (S <= 0) return NKFB_OK;
   if (!sigma || !eta || !log_val || !rho1 || !sums || !grad_acc) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (op2 && op2->kind == NKFB_OP_ISING) {
+    // (N+1)-connected U^dagger acting on psi: explicit connected batch (rho1 is not used)
+    if (psi->dtype == NKFB_F32)
+      return launch_grad_ising<float, 8>(h, psi, op2, sigma, eta, S, local_states, cv_coeff, log_val, sums, grad_acc,
+                                         st);
+    return launch_grad_ising<double, 4>(h, psi, op2, sigma, eta, S, local_states, cv_coeff, log_val, sums, grad_acc,
+                                        st);
+  }
   {
     const char *impl = getenv("NKFB_GRAD_IMPL");
     if (!(impl && strcmp(impl, "simt") == 0)) {

@@ -87,6 +87,35 @@ def test_MCState_matches_exact_like_the_reference_test(sample_Upsi, which, pdtyp
         np.testing.assert_allclose(g.imag, g_exact.imag, rtol=0.5, atol=3e-3)
 
 
+@pytest.mark.parametrize("pdtype", [complex, float])
+def test_MCState_with_an_Ising_type_U_and_U_dagger_in_the_overlap_U_estimator(pdtype):
+    """overlap_U/expect.py:101-120 takes any DiscreteJaxOperator pair: (N+1)-connected U and U^dagger
+    (`is_unitary=True`).  The estimator and the gradient on the state's own samples equal the oracle's on the
+    same samples; expect == expect_and_grad."""
+    from oracle.infidelity import infidelity_and_grad, mode_slots
+    N = 6
+    hi = nk.hilbert.Spin(0.5, N)
+    sa = nk.sampler.MetropolisLocal(hilbert=hi, n_chains_per_rank=64)
+    ma = nk.models.RBM(alpha=2, param_dtype=pdtype, stddev=0.2)
+    vs_t = nk.vqs.MCState(sampler=sa, model=ma, n_samples=2048, n_discard_per_chain=5, seed=3)
+    vs = nk.vqs.MCState(sampler=sa, model=ma, n_samples=2048, n_discard_per_chain=5, seed=4)
+    U = nkf.operator.Ising(hi, nk.graph.Chain(N), h=0.8, J=1.1).propagator(0.05)
+    oU = oops.IsingPropagator(N, oops.chain_edges(N), 0.8, 1.1, 0.05)
+    I_op = nkf.InfidelityOperator(vs_t, U=U, U_dagger=U.H, cv_coeff=-0.5, is_unitary=True)
+    st1 = vs.expect(I_op)
+    st, grad = vs.expect_and_grad(I_op)
+    assert st1.mean == pytest.approx(st.mean, abs=1e-12)
+    sigma = vs.samples.reshape(-1, N).cpu().numpy()
+    eta = vs_t.samples.reshape(-1, N).cpu().numpy()
+    U1, U2, U4 = mode_slots("upsi", oU, oU.H)
+    ref = infidelity_and_grad(_to_oracle(vs), _to_oracle(vs_t), sigma, eta, -0.5, U1, U2, U4)
+    assert st.mean == pytest.approx(1.0 - ref["F"], rel=1e-10, abs=1e-12)
+    g, gref = _flat(grad), ref["grad"].ravel()
+    if pdtype is float:
+        gref = gref.real
+    np.testing.assert_allclose(g, gref, rtol=1e-8, atol=1e-11 * max(1.0, np.abs(gref).max()))
+
+
 def test_hilbert_mismatch_and_unsupported_operator_raise():
     hi3, hi4 = nk.hilbert.Spin(0.5, 3), nk.hilbert.Spin(0.5, 4)
     ma = nk.models.RBM(alpha=1, param_dtype=complex)

@@ -154,6 +154,8 @@ def _modes(N):
         ("upsi", oops.Hadamard(N, N - 1), oops.Hadamard(N, N - 1)),
         ("standard_Uphi", oops.Rx(N, 1, 0.2), None),
         ("standard_Uphi", oops.IsingPropagator(N, e, 1.0, 1.0, 0.01), None),
+        # (N+1)-connected U and U^dagger in the overlap_U estimator (gradient over the explicit connected batch)
+        ("upsi", oops.IsingPropagator(N, e, 1.0, 1.0, 0.01), oops.IsingPropagator(N, e, 1.0, 1.0, 0.01).H),
     ]
 
 
