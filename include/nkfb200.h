@@ -117,7 +117,10 @@ int64_t nkfb_launch_count(nkfb_handle_t h);
  * Both sample the same chain from the same random numbers (they accept the same proposals up to the rounding
  * of the log-ratio); the additive kernel is always launched behind the multiplicative ones and takes over when
  * max_j (|Re b_j| + max|s| sum_i |Re W_ij|) exceeds their range. */
-enum { NKFB_OPT_SAMPLER_ALGO = 1 };
+/* NKFB_OPT_SAMPLER_SHARE (default 1): how many nkfb_sample launches of equal size the caller runs side by side
+ * on different streams (2 for the two chain families of an infidelity step).  Only a scheduling hint: it decides
+ * whether the chains beyond the last full wave of CTAs are handed to the one-chain-per-warp kernel. */
+enum { NKFB_OPT_SAMPLER_ALGO = 1, NKFB_OPT_SAMPLER_SHARE = 2 };
 int nkfb_set_option(nkfb_handle_t h, int key, int64_t value);
 
 /* ---- configurations <-> packed bits ------------------------------------- */

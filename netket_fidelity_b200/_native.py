@@ -26,6 +26,7 @@ SYMBOLS = [
 ]
 
 OPT_SAMPLER_ALGO = 1
+OPT_SAMPLER_SHARE = 2
 SAMPLER_AUTO, SAMPLER_ADDITIVE, SAMPLER_MULTIPLICATIVE = 0, 1, 2
 
 
@@ -234,6 +235,11 @@ class Handle:
         """0 auto, 1 additive (theta tracked by additions), 2 multiplicative (z = exp(-2 theta) tracked by
         complex multiplications); see include/nkfb200.h."""
         self.set_option(OPT_SAMPLER_ALGO, algo)
+
+    def set_sampler_share(self, n):
+        """Scheduling hint: `n` sampler launches of equal size run side by side on different streams (the two
+        chain families of a step: 2); see include/nkfb200.h."""
+        self.set_option(OPT_SAMPLER_SHARE, n)
 
     # ---------------------------------------------------------------- pack / unpack
     def pack(self, x, local_states):

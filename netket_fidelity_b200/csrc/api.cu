@@ -325,6 +325,10 @@ extern "C" int nkfb_set_option(nkfb_handle_t h, int key, int64_t value) {
       if (value < 0 || value > 2) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler algorithm must be 0 (auto), 1 or 2");
       h->opt_sampler_algo = (int)value;
       return NKFB_OK;
+    case NKFB_OPT_SAMPLER_SHARE:
+      if (value < 1 || value > 16) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler share must be in 1..16");
+      h->opt_sampler_share = (int)value;
+      return NKFB_OK;
     default: NKFB_FAIL(h, NKFB_ERR_INVALID, "unknown option %d", key);
   }
 }

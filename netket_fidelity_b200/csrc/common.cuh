@@ -21,6 +21,7 @@ struct nkfb_handle_s {
   void *ws4;       // scratch: connected batch (packed rows, log-amplitudes, weights) of the Ising-type U^dagger gradient
   size_t ws4_bytes;
   int opt_sampler_algo;  // NKFB_OPT_SAMPLER_ALGO
+  int opt_sampler_share; // NKFB_OPT_SAMPLER_SHARE: sampler launches of equal size that run side by side (default 1)
 };
 
 #define NKFB_CHECK_CUDA(h, call)                                                        \

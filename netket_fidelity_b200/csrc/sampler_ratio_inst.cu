@@ -1,5 +1,6 @@
 // Instantiations of the multiplicative ("ratio") plain-target sampler for one (real type, lane-group width)
 // pair.  Compiled once per pair by the Makefile:  -DNKFB_RT=float|double -DNKFB_RN=f32|f64 -DNKFB_L=4|8|16|32
+#include <algorithm>
 #include <cstdlib>
 
 #include "sampler_ratio.cuh"
@@ -38,6 +39,40 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
     if (a.site_seq != nullptr && big && !getenv("NKFB_RATIO_NOCTA")) {
       // shared site sequence: CTA-synchronous kernel, C chains per warp (z only: 4 NP words per chain)
       constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
+      // A wave of 16-warp CTAs (one per SM) lasts (steps) x (latency of one step) however full it is, so a last
+      // wave that is less than half full costs as much as a full one.  When `share` launches of this size run side
+      // by side (the two chain families of a step: NKFB_OPT_SAMPLER_SHARE = 2) and the CTAs beyond the last full
+      // wave hold few enough chains for ONE round of the one-chain-per-warp kernel (8 warps per SM and launch at
+      // 128 registers), those chains go to that kernel, whose step is about half as long.  Same Philox streams
+      // and site sequence: a chain's samples do not depend on the kernel up to single-precision rounding.
+      if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOSPLIT")) {
+        int share = h->opt_sampler_share > 0 ? h->opt_sampler_share : 1;
+        if (const char *e = getenv("NKFB_SAMPLER_SHARE")) share = atoi(e) > 0 ? atoi(e) : 1;
+        int W, TSH;
+        ratio_cta_shape(a.n_chains, CC, h->sm_count, 16, &W, &TSH);
+        const int64_t per_cta = (int64_t)CC * W;
+        const int64_t blocks = (a.n_chains + per_cta - 1) / per_cta;
+        const int64_t slots = std::max<int64_t>(1, h->sm_count / share);
+        const int64_t head = (blocks / slots) * slots * per_cta;
+        const int64_t tail = a.n_chains - head;
+        int Wh = 0;
+        if (head > 0) ratio_cta_shape(head, CC, h->sm_count, 16, &Wh, &TSH);
+        if (W == 16 && Wh == 16 && tail > 0 && tail <= (int64_t)(16 / (share < 16 ? share : 16)) * h->sm_count) {
+          const int W32 = (net->n_visible + 31) >> 5;
+          SampArgs ah = a, at = a;
+          ah.n_chains = head;
+          at.n_chains = tail;
+          at.chain_offset = a.chain_offset + (uint64_t)head;
+          at.chain_state = a.chain_state + head * W32;
+          at.samples = a.samples ? a.samples + head * a.chain_length * W32 : nullptr;
+          int rc = gl_one ? launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st)
+                          : launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+          if (rc) return rc;
+          constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
+          if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, at, ws, st);
+          return launch_ratio_pipe<NKFB_RT, NP, GW, PMB>(h, net, at, ws, st);
+        }
+      }
       if (gl_one)
         return launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       return launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);

@@ -111,6 +111,8 @@ class InfidelityStep:
         side = main if self.single_stream else self.side_stream
         if not self.single_stream:
             self.side_stream.wait_stream(main)
+        # both launches are of the same size and share the SMs: the dispatcher sizes their last wave for half a GPU
+        self.h.set_sampler_share(1 if self.single_stream else 2)
         # the two families use disjoint global chain ids: psi [0, n_chains), phi [n_chains, 2 n_chains)
         self.h.sample(psi, self.state_psi, cfg.chain_length, cfg.n_discard, self.sweep, cfg.seed,
                       cfg.local_states, op=None, chain_offset=self.chain_offset, step_offset=step_offset,
@@ -122,6 +124,7 @@ class InfidelityStep:
                           step_offset=step_offset, site_mode=cfg.site_mode, init_random=init,
                           n_accepted=self.n_accepted[1:2], out=self.eta, workspace=self.ws_phi,
                           step_offset_dev=self._step_dev)
+        self.h.set_sampler_share(1)
         if not self.single_stream:
             main.wait_stream(self.side_stream)
         if self._step_dev is not None:

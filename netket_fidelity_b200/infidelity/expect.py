@@ -60,9 +60,13 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
         side.wait_stream(main)
-        vstate.sample()
-        with torch.cuda.stream(side):
-            target.sample()
+        vstate._h.set_sampler_share(2)      # two launches of equal size side by side (include/nkfb200.h)
+        try:
+            vstate.sample()
+            with torch.cuda.stream(side):
+                target.sample()
+        finally:
+            vstate._h.set_sampler_share(1)
         main.wait_stream(side)
     sigma = vstate.samples_packed()
     eta = target.samples_packed()

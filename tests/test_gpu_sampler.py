@@ -209,6 +209,53 @@ def test_fp32_multiplicative_kernels_north_star_shape(h, algo, kernel_path, path
     assert abs(na - nb) < 0.005 * na
 
 
+def test_tail_of_a_large_launch_on_the_one_chain_per_warp_kernel(h, algo, monkeypatch):
+    """Large launches of the CTA-synchronous kernel hand the chains beyond their last full wave of CTAs to the
+    pipelined kernel when those are few (sampler_ratio_inst.cu, NKFB_OPT_SAMPLER_SHARE).  float64: the split launch
+    emits exactly the samples, final configurations and acceptance count of the unsplit one; float32 (north-star
+    shape, two launches sharing the GPU): all but a few chains agree and every chain of the tail is written."""
+    algo(2)
+    for v in ("NKFB_RATIO_NOCTA", "NKFB_RATIO_NOPIPE", "NKFB_RATIO_FORCECTA", "NKFB_RATIO_NOSPLIT"):
+        monkeypatch.delenv(v, raising=False)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    # float64: one chain per warp in the CTA kernel (launches of >= 40 chains per SM); head = 2 waves of 16-warp
+    # CTAs, tail = 8 sm + 100 chains
+    N, M = 40, 130
+    p = _net(N, M, 90, 0.3 / np.sqrt(N))
+    n_chains = 40 * sm + 100
+    got, st, nacc = _run(h, p, torch.complex128, n_chains, 2, 1, N, 4242, 0, chain_offset=3, step_offset=N + 2)
+    monkeypatch.setenv("NKFB_RATIO_NOSPLIT", "1")
+    ref, st_ref, nacc_ref = _run(h, p, torch.complex128, n_chains, 2, 1, N, 4242, 0, chain_offset=3,
+                                 step_offset=N + 2)
+    monkeypatch.delenv("NKFB_RATIO_NOSPLIT")
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(st.cpu().numpy(), st_ref.cpu().numpy())
+    assert nacc == nacc_ref
+    # the split really happened: head + tail instead of one kernel
+    l0 = h.launches
+    _run(h, p, torch.complex128, n_chains, 1, 0, N, 1, 0)
+    l_split = h.launches - l0
+    monkeypatch.setenv("NKFB_RATIO_NOSPLIT", "1")
+    l0 = h.launches
+    _run(h, p, torch.complex128, n_chains, 1, 0, N, 1, 0)
+    assert l_split > h.launches - l0          # one more kernel per range window that ran split
+    monkeypatch.delenv("NKFB_RATIO_NOSPLIT")
+    # float32, N = 100, M = 400: two chains per warp, share = 2 -> head = 3 x (sm / 2) CTAs, tail = 700 chains
+    N, M = 100, 400
+    p = _net(N, M, 11, 0.01)
+    n_chains = 3 * (sm // 2) * 32 + 700
+    h.set_sampler_share(2)
+    try:
+        a, _, na = _run(h, p, torch.complex64, n_chains, 2, 1, N, 5)
+    finally:
+        h.set_sampler_share(1)
+    monkeypatch.setenv("NKFB_RATIO_NOSPLIT", "1")
+    b, _, nb = _run(h, p, torch.complex64, n_chains, 2, 1, N, 5)
+    same = np.all(a.reshape(n_chains, -1) == b.reshape(n_chains, -1), axis=1)
+    assert same.mean() > 0.97 and same[-700:].mean() > 0.9, (same.mean(), same[-700:].mean())
+    assert abs(na - nb) < 0.005 * na
+
+
 def _z_scores(counts, p, inflate):
     S = counts.sum()
     return (counts / S - p) / np.sqrt(p * (1 - p) * inflate / S)
