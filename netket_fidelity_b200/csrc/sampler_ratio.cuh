@@ -1051,9 +1051,13 @@ inline size_t ratio_cta_smem(int NP, int C, int W, int TSH, int W32) {
 
 template <typename R, int NP, int C, int GL, int MAXW = 16, int MINB = 1>
 static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
-                            const int *site_seq, const R *a0_seq, cudaStream_t st) {
+                            const int *site_seq, const R *a0_seq, cudaStream_t st, int force_w = 0) {
   int W, TSH;
   ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
+  if (force_w > 0) {  // the launch shares the GPU with others: fewer, full CTAs instead of one CTA on every SM
+    W = force_w < MAXW ? force_w : MAXW;
+    TSH = W >= 10 ? 3 : 2;
+  }
   if (const char *e = getenv("NKFB_CTA_WARPS")) W = atoi(e) < MAXW ? atoi(e) : MAXW;  // tuning overrides
   if (const char *e = getenv("NKFB_CTA_TSH")) TSH = atoi(e);
   const size_t smem = ratio_cta_smem<R>(NP, C, W, TSH, (net->n_visible + 31) >> 5);

@@ -33,49 +33,81 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
   constexpr int GW = NP < 4 ? NP : 4;
 #if NKFB_L == 32
   if constexpr (NP <= 8) {
-    // small launches (a multi-GPU shard: fewer than ~40 chains per SM) are bound by the latency of one Metropolis
-    // step, not by throughput: there the one-chain-per-warp pipelined kernel below, which has the shorter step, wins
-    const bool big = a.n_chains >= (int64_t)40 * h->sm_count || getenv("NKFB_RATIO_NOPIPE") || getenv("NKFB_RATIO_FORCECTA");
-    if (a.site_seq != nullptr && big && !getenv("NKFB_RATIO_NOCTA")) {
-      // shared site sequence: CTA-synchronous kernel, C chains per warp (z only: 4 NP words per chain)
-      constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
-      // A wave of 16-warp CTAs (one per SM) lasts (steps) x (latency of one step) however full it is, so a last
-      // wave that is less than half full costs as much as a full one.  When `share` launches of this size run side
-      // by side (the two chain families of a step: NKFB_OPT_SAMPLER_SHARE = 2) and the CTAs beyond the last full
-      // wave hold few enough chains for ONE round of the one-chain-per-warp kernel (8 warps per SM and launch at
-      // 128 registers), those chains go to that kernel, whose step is about half as long.  Same Philox streams
-      // and site sequence: a chain's samples do not depend on the kernel up to single-precision rounding.
-      if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOSPLIT")) {
-        int share = h->opt_sampler_share > 0 ? h->opt_sampler_share : 1;
-        if (const char *e = getenv("NKFB_SAMPLER_SHARE")) share = atoi(e) > 0 ? atoi(e) : 1;
-        int W, TSH;
-        ratio_cta_shape(a.n_chains, CC, h->sm_count, 16, &W, &TSH);
-        const int64_t per_cta = (int64_t)CC * W;
-        const int64_t blocks = (a.n_chains + per_cta - 1) / per_cta;
-        const int64_t slots = std::max<int64_t>(1, h->sm_count / share);
-        const int64_t head = (blocks / slots) * slots * per_cta;
-        const int64_t tail = a.n_chains - head;
-        int Wh = 0;
-        if (head > 0) ratio_cta_shape(head, CC, h->sm_count, 16, &Wh, &TSH);
-        if (W == 16 && Wh == 16 && tail > 0 && tail <= (int64_t)(16 / (share < 16 ? share : 16)) * h->sm_count) {
-          const int W32 = (net->n_visible + 31) >> 5;
-          SampArgs ah = a, at = a;
-          ah.n_chains = head;
-          at.n_chains = tail;
-          at.chain_offset = a.chain_offset + (uint64_t)head;
-          at.chain_state = a.chain_state + head * W32;
-          at.samples = a.samples ? a.samples + head * a.chain_length * W32 : nullptr;
-          int rc = gl_one ? launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st)
-                          : launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
-          if (rc) return rc;
-          constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
-          if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, at, ws, st);
-          return launch_ratio_pipe<NKFB_RT, NP, GW, PMB>(h, net, at, ws, st);
+    // Which kernel runs how many chains (measured at the north-star shape, tools/shard_sim.py):
+    //  * CTA-synchronous kernel, CC chains per warp, 16-warp CTAs, one per SM: a WAVE of CTAs lasts (steps) x
+    //    (latency of one step) however full it is;
+    //  * one-chain-per-warp pipelined kernel, 16 warps per SM: its step is about half as long, its time grows
+    //    almost linearly with the chains beyond one round.
+    // Both have the same throughput when full, so the choice is wave arithmetic: run k FULL waves on the
+    // CTA-synchronous kernel and the remaining chains on the pipelined one, k chosen to minimise
+    //    k x wave + max(1, rounds of the rest)          (wave = 1.70 rounds at CC = 2)
+    // against ceil(waves) x wave for the CTA-synchronous kernel alone.  `share` launches of this size run side by
+    // side (the two chain families of a step: NKFB_OPT_SAMPLER_SHARE = 2), each on sm_count / share SMs.  Same
+    // Philox streams and site sequence everywhere: a chain's samples do not depend on the kernel up to
+    // single-precision rounding of the log-ratio.
+    constexpr int CC = sizeof(NKFB_RT) == 4 ? (NP <= 4 ? 4 : (NP <= 5 ? 3 : 2)) : 1;  // no register spills at 128
+    const bool pipe_ok = net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOPIPE");
+    const bool cta_ok = a.site_seq != nullptr && !getenv("NKFB_RATIO_NOCTA");
+    int share = h->opt_sampler_share > 0 ? h->opt_sampler_share : 1;
+    if (const char *e = getenv("NKFB_SAMPLER_SHARE")) share = atoi(e) > 0 ? atoi(e) : 1;
+    if (share > 16) share = 16;
+    const int64_t per_cta = (int64_t)CC * 16;
+    const int64_t blocks = (a.n_chains + per_cta - 1) / per_cta;
+    const int64_t slots = std::max<int64_t>(1, h->sm_count / share);
+    const int64_t full_waves = blocks / slots;
+    const double round_chains = 16.0 * h->sm_count / share;  // chains of this launch in one round of the pipelined kernel
+    // head: chains on the CTA-synchronous kernel (0: none, n_chains: all); w16: its CTAs are 16 warps whatever their number
+    int64_t head = 0;
+    bool w16 = false;
+    const bool legacy_big = a.n_chains >= (int64_t)40 * h->sm_count;
+    if (cta_ok && (getenv("NKFB_RATIO_FORCECTA") || !pipe_ok)) {
+      head = (legacy_big || getenv("NKFB_RATIO_FORCECTA") || getenv("NKFB_RATIO_NOPIPE")) ? a.n_chains : 0;
+    } else if (cta_ok && getenv("NKFB_RATIO_HEADWAVES")) {  // tuning override: k full waves, the rest pipelined
+      const int k = atoi(getenv("NKFB_RATIO_HEADWAVES"));
+      head = k < 0 ? a.n_chains : std::min<int64_t>(a.n_chains, (int64_t)k * slots * per_cta);
+      w16 = k >= 0;
+    } else if (cta_ok && getenv("NKFB_RATIO_NOSPLIT")) {
+      head = legacy_big ? a.n_chains : 0;
+    } else if (cta_ok && CC == 2 && sizeof(NKFB_RT) == 4) {
+      const double wave = 1.70;  // 6.65 ms per wave; 6.78 ms for 1.73 rounds, 12.9 ms for 3.46 (C4 shards of 8 and 4 GPUs)
+      double best = (double)((blocks + slots - 1) / slots) * wave;  // CTA-synchronous kernel alone
+      int64_t best_head = a.n_chains;
+      for (int64_t k = full_waves; k >= 0; --k) {
+        const int64_t hd = std::min<int64_t>(a.n_chains, k * slots * per_cta);
+        const int64_t rest = a.n_chains - hd;
+        const double t = (double)k * wave + (rest > 0 ? std::max(1.0, (double)rest / round_chains) : 0.0);
+        if (t < best * 0.98) {
+          best = t;
+          best_head = hd;
         }
       }
-      if (gl_one)
-        return launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
-      return launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      head = best_head;
+      w16 = true;   // the model counts 16-warp CTAs: (sm_count / share) of them per wave and launch
+    } else if (cta_ok && legacy_big) {
+      // other shapes: all chains on the CTA-synchronous kernel, except a last partial wave that fits one round
+      head = a.n_chains;
+      int W, TSH, Wh = 0;
+      ratio_cta_shape(a.n_chains, CC, h->sm_count, 16, &W, &TSH);
+      const int64_t hd = full_waves * slots * per_cta;
+      if (hd > 0) ratio_cta_shape(hd, CC, h->sm_count, 16, &Wh, &TSH);
+      if (W == 16 && Wh == 16 && hd < a.n_chains && (double)(a.n_chains - hd) <= round_chains) head = hd;
+    }
+    if (head > 0) {
+      SampArgs ah = a;
+      ah.n_chains = head;
+      const int fw = w16 ? 16 : 0;
+      int rc = gl_one ? launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw)
+                      : launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw);
+      if (rc || head == a.n_chains) return rc;
+      const int W32 = (net->n_visible + 31) >> 5;
+      SampArgs at = a;
+      at.n_chains = a.n_chains - head;
+      at.chain_offset = a.chain_offset + (uint64_t)head;
+      at.chain_state = a.chain_state + head * W32;
+      at.samples = a.samples ? a.samples + head * a.chain_length * W32 : nullptr;
+      constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
+      if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, at, ws, st);
+      return launch_ratio_pipe<NKFB_RT, NP, GW, PMB>(h, net, at, ws, st);
     }
   }
   if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOPIPE")) {
