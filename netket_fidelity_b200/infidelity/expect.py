@@ -84,14 +84,19 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
     _allreduce(sums)
     # n_chains = sigma_t.shape[-2] (overlap/expect.py:72): the reference hands the CHAIN LENGTH to
     # nkjax.expect as "n_chains"; mean, variance and gradient do not depend on it
-    F_stats = vstate._stats_of(L, eta.shape[-2], sums=sums)
+    # the statistics kernels go into the stream here; their read-back (a host synchronisation) waits until the
+    # gradient has been enqueued behind them, so that the GPU does not idle while the host does the statistics
+    stats_ctx = vstate._stats_begin(L, eta.shape[-2], sums=sums)
+    flat = None
+    if return_grad:
+        h.infidelity_grad(psi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff, log_val, rho1, sums,
+                          op2=op2, grad_acc=gacc)
+        _allreduce(gacc)
+        flat = h.grad_finalize(gacc, sums, vstate._flat.numel(), vstate._cdtype)
+    F_stats = vstate._stats_end(stats_ctx, L)
     I_stats = F_stats.replace(mean=1.0 - F_stats.mean)
     if not return_grad:
         return I_stats
-    h.infidelity_grad(psi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff, log_val, rho1, sums, op2=op2,
-                      grad_acc=gacc)
-    _allreduce(gacc)
-    flat = h.grad_finalize(gacc, sums, vstate._flat.numel(), vstate._cdtype)
     vstate._last_flat_grad = flat
     return I_stats, vstate._tree(flat)
 

@@ -85,12 +85,14 @@ class _RBMStateBase:
         return k, b, a
 
     def _set_params(self, params):
+        # straight into the flat device buffer; asynchronous when the source is pinned host memory (stream-ordered
+        # before the kernels that read it), an ordinary blocking copy otherwise
         k, b, a = self._views()
-        k.copy_(torch.as_tensor(params["Dense"]["kernel"]).to(self.device))
+        k.copy_(torch.as_tensor(params["Dense"]["kernel"]), non_blocking=True)
         if self._has_bias:
-            b.copy_(torch.as_tensor(params["Dense"]["bias"]).to(self.device))
+            b.copy_(torch.as_tensor(params["Dense"]["bias"]), non_blocking=True)
         if self._has_vbias:
-            a.copy_(torch.as_tensor(params["visible_bias"]).to(self.device))
+            a.copy_(torch.as_tensor(params["visible_bias"]), non_blocking=True)
         self._params_changed()
 
     def _spec(self) -> nv.RbmSpec:
@@ -293,6 +295,11 @@ class MCState(_RBMStateBase):
 
     def _stats_of(self, L, n_chains_arg, mean_override=None, sums=None):
         """nk.stats.statistics(L.reshape(n_chains_arg, -1)) with the O(S) work on the GPU."""
+        return self._stats_end(self._stats_begin(L, n_chains_arg, sums), L)
+
+    def _stats_begin(self, L, n_chains_arg, sums=None):
+        """Device half of `_stats_of`: enqueues the partial-sum kernel (and the all-gather of the other ranks' rows)
+        without waiting for it, so that a caller can put more GPU work behind it before `_stats_end` reads back."""
         S = L.numel()
         rows = int(n_chains_arg)
         cols = S // rows
@@ -305,6 +312,12 @@ class MCState(_RBMStateBase):
             from ..parallel import allgather_rows
             part = allgather_rows(part)
             rows = rows * self._world
+        return part, rows, cols, l_block, n_blocks, sums
+
+    def _stats_end(self, ctx, L):
+        """Host half of `_stats_of` (synchronises with the stream)."""
+        part, rows, cols, l_block, n_blocks, sums = ctx
+        S = L.numel()
         part = part.cpu().numpy()
         tot, tot2 = float(part[:, 0].sum()), None
         if sums is not None:
