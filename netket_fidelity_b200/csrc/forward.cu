@@ -578,7 +578,9 @@ static int launch_grad_ising(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_
   const int N = psi->n_visible, C = N + 1, W32 = (N + 31) >> 5;
   // scratch per sample: C packed rows, C log-amplitudes, C + 1 weights; chunks of at most ~256 MiB
   const size_t per_sample = (size_t)C * (W32 * 4 + 2 * sizeof(cx<R>)) + sizeof(cx<R>);
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(S, (int64_t)((size_t(256) << 20) / per_sample)));
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(S, (int64_t)((size_t(256) << 20) / per_sample)));
+  if (const char *e = getenv("NKFB_ISING_GRAD_CHUNK"))  // testing: force several chunks on small batches
+    chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, atoll(e)));
   const size_t need = per_sample * (size_t)chunk + 64;
   if (h->ws4_bytes < need) {
     if (h->ws4) cudaFree(h->ws4);

@@ -190,6 +190,26 @@ def test_infidelity_fwd_and_grad_fixed_batch(h, N, M, S, cd, cv):
         assert rel_err(g, gref) <= tol * 20, (mode, U, rel_err(g, gref))
 
 
+@pytest.mark.parametrize("cd", [torch.complex128, torch.complex64])
+def test_ising_type_U_dagger_gradient_in_several_chunks(h, cd, monkeypatch):
+    """The (N+1)-connected U^dagger gradient walks the batch in chunks of handle-owned scratch: a chunk length that
+    does not divide S (ragged last chunk) gives the oracle's gradient as well."""
+    rng = np.random.default_rng(7)
+    N, M, S = 33, 70, 300
+    psi, phi = _net(N, M, 21, 0.05), _net(N, M, 22, 0.05)
+    sigma, eta = _rand_states(rng, S, N), _rand_states(rng, S, N)
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    U = oops.IsingPropagator(N, oops.chain_edges(N), 0.9, 1.2, 0.02)
+    U1, U2, U4 = mode_slots("upsi", U, U.H)
+    ref = infidelity_and_grad(psi, phi, sigma, eta, -0.5, U1, U2, U4)
+    a, b = to_rbmspec(psi, cd), to_rbmspec(phi, cd)
+    lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, -0.5, to_opspec(U1), to_opspec(U2), to_opspec(U4))
+    monkeypatch.setenv("NKFB_ISING_GRAD_CHUNK", "37")
+    gacc = h.infidelity_grad(a, sp, ep, LS, -0.5, lv, rho1, sums, to_opspec(U2))
+    g = h.grad_finalize(gacc, sums, a.n_params, cd).cpu().numpy()
+    assert rel_err(g, ref["grad"].ravel()) <= TOL[cd] * 20
+
+
 def test_gradient_without_visible_bias(h):
     rng = np.random.default_rng(1)
     N, S = 4, 112
