@@ -122,8 +122,9 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream ON `device` (the handle's device, not the process's current device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ls(local_states):
@@ -219,6 +220,15 @@ class Handle:
         except Exception:
             pass
 
+    def _stream(self):
+        return _stream(self.device)
+
+    def _on_device(self, *tensors):
+        """Arguments must live on the handle's device: a pointer of another GPU would fault or, worse, alias."""
+        for t in tensors:
+            if t is not None and (not t.is_cuda or t.device.index != self.device.index):
+                raise NkfbError(f"tensor on {t.device} passed to the handle of {self.device}")
+
     def _check(self, rc, what):
         if rc != 0:
             msg = self.lib.nkfb_last_error(self.h)
@@ -248,14 +258,14 @@ class Handle:
         B = x.numel() // N
         out = torch.empty((B, (N + 31) // 32), dtype=torch.int32, device=x.device)
         self._check(self.lib.nkfb_pack(self.h, _ptr(x), real_dtype_code(x.dtype), B, N, _ls(local_states),
-                                       _ptr(out), _stream()), "nkfb_pack")
+                                       _ptr(out), self._stream()), "nkfb_pack")
         return out
 
     def unpack(self, packed, N, local_states, dtype=torch.float64):
         B = packed.shape[0]
         out = torch.empty((B, N), dtype=dtype, device=packed.device)
         self._check(self.lib.nkfb_unpack(self.h, _ptr(packed), B, N, _ls(local_states), _ptr(out),
-                                         real_dtype_code(dtype), _stream()), "nkfb_unpack")
+                                         real_dtype_code(dtype), self._stream()), "nkfb_unpack")
         return out
 
     # ---------------------------------------------------------------- connected elements
@@ -268,17 +278,18 @@ class Handle:
         mels = torch.empty((B, Cn), dtype=torch.complex128, device=x.device)
         s = op.struct()
         self._check(self.lib.nkfb_conn(self.h, C.byref(s), _ptr(x), real_dtype_code(x.dtype), B, N,
-                                       _ls(local_states), _ptr(xp), _ptr(mels), _stream()), "nkfb_conn")
+                                       _ls(local_states), _ptr(xp), _ptr(mels), self._stream()), "nkfb_conn")
         return xp, mels
 
     # ---------------------------------------------------------------- log amplitudes
     def logpsi(self, net: RbmSpec, packed, local_states, op: OpSpec | None = None):
         B = packed.shape[0]
+        self._on_device(net.kernel, packed)
         out = torch.empty((B,), dtype=net.kernel.dtype, device=packed.device)
         ns = net.struct()
         os_ = op.struct() if op is not None else None
         self._check(self.lib.nkfb_logpsi(self.h, C.byref(ns), C.byref(os_) if os_ is not None else None,
-                                         _ptr(packed), B, _ls(local_states), _ptr(out), _stream()), "nkfb_logpsi")
+                                         _ptr(packed), B, _ls(local_states), _ptr(out), self._stream()), "nkfb_logpsi")
         return out
 
     # ---------------------------------------------------------------- sampler
@@ -287,6 +298,7 @@ class Handle:
                n_accepted=None, out=None, workspace=None, step_offset_dev=None):
         """step_offset_dev: optional device int64[1] added to step_offset by the kernels (CUDA-graph replays)."""
         n_chains, W32 = chain_state.shape
+        self._on_device(net.kernel, chain_state, out, n_accepted, workspace, step_offset_dev)
         if out is None:
             out = torch.empty((n_chains, chain_length, W32), dtype=torch.int32, device=chain_state.device)
         cfg = SampleCfgT()
@@ -303,7 +315,7 @@ class Handle:
         ns = net.struct()
         os_ = op.struct() if op is not None else None
         self._check(self.lib.nkfb_sample(self.h, C.byref(ns), C.byref(os_) if os_ is not None else None,
-                                         C.byref(cfg), _ptr(chain_state), _ptr(out), _ptr(n_accepted), _stream()),
+                                         C.byref(cfg), _ptr(chain_state), _ptr(out), _ptr(n_accepted), self._stream()),
                     "nkfb_sample")
         return out
 
@@ -317,6 +329,7 @@ class Handle:
                        op4=None, sums=None):
         S = sigma.shape[0]
         dev = sigma.device
+        self._on_device(psi.kernel, phi.kernel, sigma, eta, sums)
         cd, rd = psi.kernel.dtype, real_dtype(psi.code)
         log_val = torch.empty((S,), dtype=cd, device=dev)
         L = torch.empty((S,), dtype=rd, device=dev)
@@ -331,13 +344,14 @@ class Handle:
         cv = float("nan") if cv_coeff is None else float(cv_coeff)
         self._check(self.lib.nkfb_infidelity_fwd(self.h, C.byref(a), C.byref(b), ref(o1), ref(o2), ref(o4),
                                                  _ptr(sigma), _ptr(eta), S, _ls(local_states), cv, _ptr(log_val),
-                                                 _ptr(L), _ptr(rho1), _ptr(sums), _stream()),
+                                                 _ptr(L), _ptr(rho1), _ptr(sums), self._stream()),
                     "nkfb_infidelity_fwd")
         return log_val, L, rho1, sums
 
     def infidelity_grad(self, psi: RbmSpec, sigma, eta, local_states, cv_coeff, log_val, rho1, sums, op2=None,
                         grad_acc=None):
         S = sigma.shape[0]
+        self._on_device(psi.kernel, sigma, eta, log_val, rho1, sums, grad_acc)
         if grad_acc is None:
             grad_acc = torch.zeros((2 * psi.n_params,), dtype=torch.float64, device=sigma.device)
         a = psi.struct()
@@ -345,7 +359,7 @@ class Handle:
         cv = float("nan") if cv_coeff is None else float(cv_coeff)
         self._check(self.lib.nkfb_infidelity_grad(self.h, C.byref(a), C.byref(o2) if o2 is not None else None,
                                                   _ptr(sigma), _ptr(eta), S, _ls(local_states), cv, _ptr(log_val),
-                                                  _ptr(rho1), _ptr(sums), _ptr(grad_acc), _stream()),
+                                                  _ptr(rho1), _ptr(sums), _ptr(grad_acc), self._stream()),
                     "nkfb_infidelity_grad")
         return grad_acc
 
@@ -357,20 +371,20 @@ class Handle:
         ns = net.struct()
         weights = weights.to(complex_dtype(net.code)).contiguous()
         self._check(self.lib.nkfb_weighted_score(self.h, C.byref(ns), _ptr(packed), S, _ls(local_states),
-                                                 _ptr(weights), _ptr(acc), _stream()), "nkfb_weighted_score")
+                                                 _ptr(weights), _ptr(acc), self._stream()), "nkfb_weighted_score")
         return acc
 
     def grad_finalize(self, grad_acc, sums, P, dtype):
         out = torch.empty((P,), dtype=dtype, device=grad_acc.device)
         self._check(self.lib.nkfb_grad_finalize(self.h, _ptr(grad_acc), _ptr(sums), P, real_dtype_code(dtype),
-                                                _ptr(out), _stream()), "nkfb_grad_finalize")
+                                                _ptr(out), self._stream()), "nkfb_grad_finalize")
         return out
 
     # ---------------------------------------------------------------- statistics
     def chain_stats(self, L, rows, cols, l_block, n_blocks):
         out = torch.empty((rows, 3 + n_blocks), dtype=torch.float64, device=L.device)
         self._check(self.lib.nkfb_chain_stats(self.h, _ptr(L), real_dtype_code(L.dtype), rows, cols, l_block,
-                                              n_blocks, _ptr(out), _stream()), "nkfb_chain_stats")
+                                              n_blocks, _ptr(out), self._stream()), "nkfb_chain_stats")
         return out
 
     # ---------------------------------------------------------------- Renyi-2
@@ -384,7 +398,7 @@ class Handle:
         sums = torch.zeros((8,), dtype=torch.float64, device=dev)
         ns = net.struct()
         self._check(self.lib.nkfb_renyi2(self.h, C.byref(ns), _ptr(samples), S_half, _ptr(mask_words),
-                                         _ls(local_states), _ptr(scratch), _ptr(lp), _ptr(q), _ptr(sums), _stream()),
+                                         _ls(local_states), _ptr(scratch), _ptr(lp), _ptr(q), _ptr(sums), self._stream()),
                     "nkfb_renyi2")
         return q, sums
 
@@ -393,12 +407,12 @@ class Handle:
         P = params.numel()
         self._check(self.lib.nkfb_optimizer_update(self.h, kind, real_dtype_code(params.dtype), _ptr(params),
                                                    _ptr(grad), _ptr(m), _ptr(v), P, lr, b1, b2, eps, t,
-                                                   1 if real_params else 0, _stream()), "nkfb_optimizer_update")
+                                                   1 if real_params else 0, self._stream()), "nkfb_optimizer_update")
 
     # ---------------------------------------------------------------- micro-benchmarks
     def microbench(self, kind, iters=4096):
         v = C.c_double()
-        self._check(self.lib.nkfb_microbench(self.h, kind, iters, C.byref(v), _stream()), "nkfb_microbench")
+        self._check(self.lib.nkfb_microbench(self.h, kind, iters, C.byref(v), self._stream()), "nkfb_microbench")
         return v.value
 
 

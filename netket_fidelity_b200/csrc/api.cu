@@ -195,9 +195,14 @@ extern "C" int nkfb_create(int device, nkfb_handle_t *out) {
     delete h;
     return NKFB_ERR_UNSUPPORTED;
   }
-  if (cudaSetDevice(device) != cudaSuccess) {
-    delete h;
-    return NKFB_ERR_CUDA;
+  {
+    // initialise the context of `device` without leaving the caller's current device changed
+    NkfbDeviceGuard guard(device);
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device || cudaFree(nullptr) != cudaSuccess) {
+      delete h;
+      return NKFB_ERR_CUDA;
+    }
   }
   *out = h;
   return NKFB_OK;
@@ -205,6 +210,7 @@ extern "C" int nkfb_create(int device, nkfb_handle_t *out) {
 
 extern "C" int nkfb_destroy(nkfb_handle_t h) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (h->ws) cudaFree(h->ws);
   if (h->ws2) cudaFree(h->ws2);
   if (h->ws3) cudaFree(h->ws3);
@@ -226,6 +232,7 @@ static int grid_for(int64_t total, int sm) {
 extern "C" int nkfb_pack(nkfb_handle_t h, const void *x, int x_dtype, int64_t B, int N, const double ls[2],
                          uint32_t *packed, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (B <= 0) return NKFB_OK;
   if (!x || !packed || N < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad pack arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -244,6 +251,7 @@ extern "C" int nkfb_pack(nkfb_handle_t h, const void *x, int x_dtype, int64_t B,
 extern "C" int nkfb_unpack(nkfb_handle_t h, const uint32_t *packed, int64_t B, int N, const double ls[2], void *x,
                            int x_dtype, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (B <= 0) return NKFB_OK;
   if (!x || !packed || N < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad unpack arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -261,6 +269,7 @@ extern "C" int nkfb_unpack(nkfb_handle_t h, const uint32_t *packed, int64_t B, i
 extern "C" int nkfb_conn(nkfb_handle_t h, const nkfb_op_t *op, const void *x, int x_dtype, int64_t B, int N,
                          const double ls[2], void *xp, void *mels, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!op || (op->kind != NKFB_OP_GATE && op->kind != NKFB_OP_ISING))
     NKFB_FAIL(h, NKFB_ERR_INVALID, "conn needs a GATE or ISING operator");
   if (B <= 0) return NKFB_OK;
@@ -304,6 +313,7 @@ extern "C" int nkfb_conn(nkfb_handle_t h, const nkfb_op_t *op, const void *x, in
 extern "C" int nkfb_chain_stats(nkfb_handle_t h, const void *L, int dtype, int64_t rows, int64_t cols,
                                 int64_t l_block, int64_t n_blocks, double *out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!L || !out || rows < 1 || cols < 1 || l_block < 1 || n_blocks < 0 || n_blocks * l_block > cols)
     NKFB_FAIL(h, NKFB_ERR_INVALID, "bad chain_stats arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -320,6 +330,7 @@ extern "C" int nkfb_chain_stats(nkfb_handle_t h, const void *L, int dtype, int64
 
 extern "C" int nkfb_set_option(nkfb_handle_t h, int key, int64_t value) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   switch (key) {
     case NKFB_OPT_SAMPLER_ALGO:
       if (value < 0 || value > 2) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler algorithm must be 0 (auto), 1 or 2");
@@ -398,6 +409,7 @@ extern "C" int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void 
                                      void *v, int64_t P, double lr, double b1, double b2, double eps, int64_t t,
                                      int real_params, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!params || !grad || P <= 0 || (kind == 1 && (!m || !v)) || t < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad optimizer arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const double c1 = 1.0 - pow(b1, (double)t), c2 = 1.0 - pow(b2, (double)t);

@@ -24,6 +24,19 @@ struct nkfb_handle_s {
   int opt_sampler_share; // NKFB_OPT_SAMPLER_SHARE: sampler launches of equal size that run side by side (default 1)
 };
 
+// Every entry point runs on the handle's device whatever the caller's current device is, and restores the latter.
+struct NkfbDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit NkfbDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~NkfbDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define NKFB_DEVICE_GUARD(h) NkfbDeviceGuard nkfb_device_guard__((h)->device)
+
 #define NKFB_CHECK_CUDA(h, call)                                                        \
   do {                                                                                  \
     cudaError_t e__ = (call);                                                           \

@@ -626,6 +626,7 @@ using namespace nkfb;
 extern "C" int nkfb_logpsi(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op, const uint32_t *packed,
                            int64_t B, const double local_states[2], void *out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   int rc = check_net(h, net);
   if (rc) return rc;
   rc = check_op(h, op, net->n_visible);
@@ -656,6 +657,7 @@ extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const
                                    const double local_states[2], double cv_coeff, void *log_val, void *L,
                                    void *rho1, double *sums, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   int rc = check_net(h, psi);
   if (rc) return rc;
   rc = check_net(h, phi);
@@ -692,6 +694,7 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
                                     const double local_states[2], double cv_coeff, const void *log_val,
                                     const void *rho1, const double *sums, double *grad_acc, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   int rc = check_net(h, psi);
   if (rc) return rc;
   rc = check_op(h, op2, psi->n_visible);
@@ -724,6 +727,7 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
 extern "C" int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *packed, int64_t S,
                                    const double local_states[2], const void *weights, double *acc, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   int rc = check_net(h, net);
   if (rc) return rc;
   if (S <= 0) return NKFB_OK;
@@ -739,6 +743,7 @@ extern "C" int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const
 extern "C" int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums, int64_t P, int dtype,
                                   void *grad_out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!grad_acc || !sums || !grad_out || P <= 0) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad finalize arguments");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (int)std::min<int64_t>((2 * P + 255) / 256, 1024);

@@ -51,6 +51,7 @@ extern "C" int nkfb_renyi2(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_
                            const uint32_t *mask, const double local_states[2], uint32_t *scratch,
                            void *scratch_logpsi, void *q, double *sums, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!net || !samples || !mask || !scratch || !scratch_logpsi || !q || !sums)
     NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
   if (S_half <= 0) return NKFB_OK;

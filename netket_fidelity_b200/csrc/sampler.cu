@@ -486,6 +486,7 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
                            const nkfb_sample_cfg_t *cfg, uint32_t *chain_state, uint32_t *samples,
                            unsigned long long *n_accepted, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
   if (!net || !net->kernel || !cfg) NKFB_FAIL(h, NKFB_ERR_INVALID, "null argument");
   if (net->dtype != NKFB_F32 && net->dtype != NKFB_F64) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM dtype");
   if (net->n_visible < 1 || net->n_hidden < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM shape");

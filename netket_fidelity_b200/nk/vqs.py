@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from .. import _native as nv
+from .. import parallel as par
 from .stats import Stats, stats_from_partials
 
 _seed_counter = itertools.count()
@@ -49,7 +50,8 @@ class _RBMStateBase:
         self._N = N
         self._ls = tuple(hilbert.local_states)
         if seed is None:
-            seed = int.from_bytes(os.urandom(4), "little") + next(_seed_counter)
+            # default seed: drawn on rank 0 and broadcast, so that every rank initialises the SAME parameters
+            seed = par.broadcast_seed(int.from_bytes(os.urandom(4), "little") + next(_seed_counter))
         self._seed = int(seed)
         self._unitary = None
         if variables is not None:
@@ -206,7 +208,8 @@ class MCState(_RBMStateBase):
 
         # --- parameters
         if seed is None:
-            seed = int.from_bytes(os.urandom(4), "little") + next(_seed_counter)
+            # default seed: drawn on rank 0 and broadcast, so that every rank initialises the SAME parameters
+            seed = par.broadcast_seed(int.from_bytes(os.urandom(4), "little") + next(_seed_counter))
         self._seed = int(seed)
         self._sampler_seed = int(sampler_seed) if sampler_seed is not None else (self._seed * 2654435761 + 12345) % (1 << 63)
         self._unitary = None

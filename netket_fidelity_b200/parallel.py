@@ -32,6 +32,22 @@ def shard_chains(n_chains_total: int, world: int, rank: int):
     return rank * n_local, n_local
 
 
+def broadcast_seed(seed, group=None) -> int:
+    """The seed every rank must use for a default-seeded (seed=None) state: rank 0's value.
+
+    NetKet broadcasts the PRNG key of rank 0 before `model.init`, so that the replicated parameters start
+    identical on all ranks; an independent os.urandom draw per rank would make every rank sample and
+    differentiate a DIFFERENT state while their sums are all-reduced together.  Single rank: returned as is."""
+    world, _ = world_info(group)
+    if world == 1:
+        return int(seed)
+    d = torch.distributed
+    dev = torch.device("cuda", torch.cuda.current_device()) if d.get_backend(group) == "nccl" else torch.device("cpu")
+    box = torch.tensor([int(seed) & ((1 << 62) - 1)], dtype=torch.int64, device=dev)
+    d.broadcast(box, src=d.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(box.item())
+
+
 def allreduce_sum_(t: torch.Tensor, group=None):
     world, _ = world_info(group)
     if world > 1:

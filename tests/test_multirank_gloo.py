@@ -136,3 +136,33 @@ def test_shard_chains_errors():
     assert par.shard_chains(16, 4, 3) == (12, 4)
     with pytest.raises(ValueError):
         par.shard_chains(10, 4, 0)
+
+
+def _seed_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from netket_fidelity_b200 import parallel as par
+    from netket_fidelity_b200.nk.models import RBM
+    local_draw = 1000 + 17 * rank                       # what os.urandom would give: different on every rank
+    seed = par.broadcast_seed(local_draw)
+    params = RBM(alpha=2, param_dtype=complex).init(seed, 6, torch.device("cpu"))
+    flat = torch.cat([torch.view_as_real(params["Dense"]["kernel"].reshape(-1).to(torch.complex128)).reshape(-1)])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    q.put((rank, seed, bool(all(torch.equal(g, gathered[0]) for g in gathered))))
+    dist.destroy_process_group()
+
+
+def test_default_seed_is_broadcast_from_rank_zero():
+    """seed=None states (nk/vqs.py) draw their seed on rank 0 only: every rank initialises identical parameters
+    (NetKet broadcasts the PRNG key of rank 0); ADVICE r1, medium."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, 1000, True), (1, 1000, True)]
