@@ -230,8 +230,11 @@ int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void *params, co
                           int64_t t, int real_params, void *stream);
 
 /* ---- MUFU / FP32 micro-benchmarks (roofline denominators) ---------------- */
-/* Runs `iters` dependent-free MUFU.EX2 (kind 0), MUFU.COS (1), MUFU.LG2 (2) or FFMA (3)
- * per thread on a full grid; returns operations/second measured with CUDA events. */
+/* Pipe-rate micro-benchmarks behind the roofline denominators bench.py reports (MEASURED_PEAKS.json holds only the
+ * HBM and bf16 tensor peaks): `iters` rounds of 8 independent chains per thread on a full grid of
+ * kind 0 MUFU.EX2, 1 MUFU.COS, 2 MUFU.LG2, 3 FFMA with immediate operands, 4 FFMA with three register operands,
+ * 5 packed FFMA2 (two FMAs per lane and instruction; counted as FMAs), 6 DFMA (FP64).
+ * Returns operations (FMAs) per second measured with CUDA events. */
 int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops_per_second, void *stream);
 
 #ifdef __cplusplus

@@ -136,6 +136,8 @@ __global__ void microbench_kernel(int iters, float *sink) {
   float e = a + 0.1f, f = b + 0.1f, g = c + 0.1f, hh = d + 0.1f;
   const float m1 = 0.999f + 1e-9f * (float)iters, m2 = 0.001f + 1e-9f * (float)iters;  // runtime values: no immediates
   float2 A2 = make_float2(a, e), B2 = make_float2(b, f), C2 = make_float2(c, g), D2 = make_float2(d, hh);
+  double da = a, db = b, dc = c, dd = d, de = e, df = f, dg = g, dh = hh;
+  const double dm1 = m1, dm2 = m2;
   for (int i = 0; i < iters; ++i) {
     if (KIND == 0) {
       a = mufu_ex2(a); b = mufu_ex2(b); c = mufu_ex2(c); d = mufu_ex2(d);
@@ -156,6 +158,9 @@ __global__ void microbench_kernel(int iters, float *sink) {
     } else if (KIND == 4) {  // three-register FFMA
       a = fmaf(a, m1, m2); b = fmaf(b, m1, m2); c = fmaf(c, m1, m2); d = fmaf(d, m1, m2);
       e = fmaf(e, m1, m2); f = fmaf(f, m1, m2); g = fmaf(g, m1, m2); hh = fmaf(hh, m1, m2);
+    } else if (KIND == 6) {  // FP64 FMA (the parity path's pipe): 8 independent DFMA chains kept in double
+      da = fma(da, dm1, dm2); db = fma(db, dm1, dm2); dc = fma(dc, dm1, dm2); dd = fma(dd, dm1, dm2);
+      de = fma(de, dm1, dm2); df = fma(df, dm1, dm2); dg = fma(dg, dm1, dm2); dh = fma(dh, dm1, dm2);
     } else {  // KIND 5: packed FFMA2 (2 FMAs per lane per instruction), 8 instructions = 16 FMAs
       float2 A = make_float2(a, b), B = make_float2(c, d), Cc = make_float2(e, f), D = make_float2(g, hh);
       const float2 M1 = make_float2(m1, m1), M2 = make_float2(m2, m2);
@@ -165,6 +170,7 @@ __global__ void microbench_kernel(int iters, float *sink) {
     }
   }
   float r = a + b + c + d + e + f + g + hh + A2.x + A2.y + B2.x + B2.y + C2.x + C2.y + D2.x + D2.y;
+  if (KIND == 6) r += (float)(da + db + dc + dd + de + df + dg + dh);
   if (r == 123.456f) sink[0] = r;
 }
 
@@ -362,6 +368,7 @@ extern "C" int nkfb_microbench(nkfb_handle_t h, int kind, int iters, double *ops
       case 2: microbench_kernel<2><<<grid, block, 0, st>>>(iters, sink); break;
       case 3: microbench_kernel<3><<<grid, block, 0, st>>>(iters, sink); break;
       case 4: microbench_kernel<4><<<grid, block, 0, st>>>(iters, sink); break;
+      case 6: microbench_kernel<6><<<grid, block, 0, st>>>(iters, sink); break;
       default: microbench_kernel<5><<<grid, block, 0, st>>>(iters, sink); break;
     }
     h->launches++;

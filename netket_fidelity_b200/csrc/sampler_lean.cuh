@@ -1,0 +1,357 @@
+// Lean form of the CTA-synchronous multiplicative sampler (sampler_ratio.cuh: sample_ratio_cta_kernel) for the
+// shared site sequence, single precision, M on 32 lanes.  Same algorithm, same Philox streams, same row staging
+// (cp.async, double-buffered chunks of T steps); what changes is the INSTRUCTION BUDGET of a Metropolis step.
+//
+// Measured on B200 (profiles/r02_sampler_notes.md): a packed FFMA2 / FMUL2 / FADD2 holds the issue port of its SM
+// sub-partition for two cycles, every other instruction for one, and the round-1 kernel issued 108 packed + 150 other
+// instructions per warp-step of two chains -- 366 issue cycles of which 150 were bookkeeping.  Giving a sub-partition
+// more warps (one chain per warp, 24-32 warps per SM) or fewer chains (28 per CTA) does not change the rate: the
+// issue port, not latency, is the bound.  So this kernel removes instructions:
+//   * one 16-byte table entry per step, written when the rows of its chunk are staged: byte offset of the
+//     configuration word, bit mask, and A_site already in the fixed-point units of the decision -- no shifts, no
+//     address arithmetic, no float threshold per chain and step;
+//   * log2 u is staged as a fixed-point integer at refill time; the whole threshold is folded into lane 0's addend
+//     of the integer REDUX, so the decision is `sum > 0` on a uniform register: a uniform branch, no
+//     BSSY / BSYNC pair, no predicate built from a per-thread compare;
+//   * the +-60 clamp of the addend is the saturation of F2I followed by one arithmetic shift (2^26 fixed point
+//     -> 2^20), and the rounding offset rides in the FFMA that forms the addend;
+//   * all lanes store the flipped configuration word (same value, same address): no lane-0 predicate and no
+//     __syncwarp between steps;
+//   * the steps of a chunk are unrolled with immediate row offsets; sweep boundaries, the partial first / last
+//     chunk and the RNG refill are checked once per chunk, not once per step.
+#pragma once
+
+#include "sampler_ratio.cuh"
+
+namespace nkfb {
+
+constexpr int LEAN_T = 8;                     // steps per chunk
+constexpr int LEAN_TSH = 3;
+constexpr int LEAN_SB = 128;                  // steps per RNG batch
+constexpr float LEAN_FX = 67108864.0f;        // 2^26: fixed point of the addend inside F2I; >> 6 afterwards
+constexpr float LEAN_FT = 1048576.0f;         // 2^20: fixed point of the thresholds
+
+inline size_t lean_smem_bytes(int NP, int C, int W, int W32) {
+  return (size_t)4 * LEAN_T * 4 * NP * 32 * 4 + (size_t)2 * LEAN_T * 16 + (size_t)W * C * LEAN_SB * 4 + (size_t)W * C * W32 * 4;
+}
+
+template <int NP, int C, int GL, int UNR>
+__global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float> net, const float *ws, const float s0,
+                                                                   const float s1, SampArgs a, const int *site_seq,
+                                                                   const float *a0_seq) {
+  using P = P2<float>;
+  using V = float2;
+  constexpr int L = 32, T = LEAN_T, SB = LEAN_SB;
+  constexpr int NG = (NP + GL - 1) / GL;
+  constexpr int ROW = 4 * NP * L;  // floats per (table, site) row
+  extern __shared__ __align__(16) unsigned char lean_smem[];
+  if (!samp_window_ok(a)) return;  // uniform over the grid: taken before any barrier
+  samp_resolve_offset(a);
+  const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  float *rows = reinterpret_cast<float *>(lean_smem);                              // [2][T][2][ROW]
+  int4 *steptab = reinterpret_cast<int4 *>(rows + (size_t)4 * T * ROW);           // [2][T]
+  int *s_tu = reinterpret_cast<int *>(steptab + 2 * T) + (size_t)warp * C * SB;   // [C][SB] of this warp
+  volatile uint32_t *sigx =
+      reinterpret_cast<uint32_t *>(reinterpret_cast<int *>(steptab + 2 * T) + (size_t)W * C * SB) + warp * C * W32;
+  const int64_t chain0 = ((int64_t)blockIdx.x * W + warp) * C;
+  const V one = P::mk(1.0f, 1.0f);
+  const int n_valid = a.n_chains - chain0 >= C ? C : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
+
+  // ---- configurations
+  for (int idx = lane; idx < C * W32; idx += 32) {
+    const int c = idx / W32, w = idx - c * W32;
+    uint32_t v = 0;
+    if (c < n_valid) {
+      if (a.init_random) {
+        u32x4 ctr = {(uint32_t)(w >> 2), 0u, (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_INIT};
+        v = sel4(philox4x32_10(ctr, a.k0, a.k1), w & 3);
+      } else {
+        v = a.chain_state[(chain0 + c) * W32 + w];
+      }
+      const int nb = N - 32 * w;
+      if (nb < 32) v &= (1u << nb) - 1u;
+    }
+    sigx[idx] = v;
+  }
+  __syncwarp();
+
+  const int n_sweeps = a.n_discard + a.chain_length;
+  const uint32_t n_steps = (uint32_t)n_sweeps * (uint32_t)a.sweep_size;
+  const uint32_t phase = (uint32_t)(a.step_offset & (uint64_t)(SB - 1));
+  const uint64_t batch0 = a.step_offset - phase;
+
+  // floor(2^20 log2 u) of the batch that starts `pos0` steps after batch0, for the C chains of this warp; a chain slot
+  // without a chain gets a threshold nothing reaches
+  auto refill = [&](uint32_t pos0) {
+    __syncwarp();
+    const uint64_t blk = ((batch0 + (uint64_t)pos0) >> 2) + (uint64_t)lane;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      u32x4 ctr = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)(a.chain_offset + chain0 + c), (uint32_t)TAG_UNIFORM};
+      const u32x4 ru = philox4x32_10(ctr, a.k0, a.k1);
+      int4 t;
+      t.x = __float2int_rd(SMath<float>::log2u(ru.x) * LEAN_FT);
+      t.y = __float2int_rd(SMath<float>::log2u(ru.y) * LEAN_FT);
+      t.z = __float2int_rd(SMath<float>::log2u(ru.z) * LEAN_FT);
+      t.w = __float2int_rd(SMath<float>::log2u(ru.w) * LEAN_FT);
+      if (c >= n_valid) t = make_int4(1 << 30, 1 << 30, 1 << 30, 1 << 30);
+      *reinterpret_cast<int4 *>(s_tu + c * SB + 4 * lane) = t;
+    }
+    __syncwarp();
+  };
+  // request the 2 T rows of chunk qn (positions qn T .. qn T + T - 1) into buffer qn & 1, and write its step table
+  auto issue_rows = [&](uint32_t qn) {
+    for (int r = warp; r < 2 * T; r += W) {
+      const int tt = r >> 1, tab = r & 1;
+      const int64_t sidx = ((int64_t)qn << LEAN_TSH) + tt - (int64_t)phase;
+      const uint32_t sc = sidx < 0 ? 0u : (sidx >= (int64_t)n_steps ? n_steps - 1 : (uint32_t)sidx);
+      const int st = __ldg(site_seq + sc);
+      const char *src = reinterpret_cast<const char *>(ws + (size_t)(tab * N + st) * ROW);
+      char *dst = reinterpret_cast<char *>(rows + ((((qn & 1u) << LEAN_TSH) + tt) * 2 + tab) * ROW);
+      for (int off = lane * 16; off < (int)(ROW * sizeof(float)); off += 512) cp_async16(dst + off, src + off);
+    }
+    if (threadIdx.x < T) {
+      const int tt = threadIdx.x;
+      const int64_t sidx = ((int64_t)qn << LEAN_TSH) + tt - (int64_t)phase;
+      const uint32_t sc = sidx < 0 ? 0u : (sidx >= (int64_t)n_steps ? n_steps - 1 : (uint32_t)sidx);
+      const int st = __ldg(site_seq + sc);
+      steptab[((qn & 1u) << LEAN_TSH) + tt] =
+          make_int4((st >> 5) * 4, (int)(1u << (st & 31)), __float2int_rn(__ldg(a0_seq + sc) * LEAN_FT), st);
+    }
+  };
+
+  V Zr[C][NP], Zi[C][NP];
+  float nlg[C];  // 32 - 2^26 (this lane's sum_j log2 |1 + z_j|^2): the constant term of the fixed-point addend
+  unsigned n_acc = 0;
+
+  // z <- z * row (in place); returns this lane's sum_j log2 |1 + z_j|^2.  rp: shared memory, lane offset applied.
+  auto multiply = [&](V (&zr)[NP], V (&zi)[NP], const float *rp, bool want_log) -> float {
+    float acc = 0.0f;
+#pragma unroll
+    for (int gq = 0; gq < NG; ++gq) {
+      constexpr int GS = GL;
+      V qlo[GS], qhi[GS], m[GS];
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int p = gq * GL + i;
+        if (p < NP) {
+          const float4 q = *reinterpret_cast<const float4 *>(rp + 4 * L * p);
+          qlo[i] = make_float2(q.x, q.y);
+          qhi[i] = make_float2(q.z, q.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GS; ++i) {
+        const int p = gq * GL + i;
+        if (p < NP) cmul_inplace(zr[p], zi[p], qlo[i], qhi[i]);
+      }
+      if (want_log) {
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = add2_(zr[gq * GL + i], one);
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = P::mul(m[i], m[i]);
+#pragma unroll
+        for (int i = 0; i < GS; ++i)
+          if (gq * GL + i < NP) m[i] = P::fma(zi[gq * GL + i], zi[gq * GL + i], m[i]);
+#pragma unroll
+        for (int st = 1; st < GS; st <<= 1)
+#pragma unroll
+          for (int i = 0; i < GS; ++i)
+            if (i % (2 * st) == 0 && i + st < GS && gq * GL + i + st < NP) m[i] = P::mul(m[i], m[i + st]);
+        const float lv = P::lg2(m[0].x * m[0].y);
+        acc = gq == 0 ? lv : acc + lv;
+      }
+    }
+    return acc;
+  };
+
+  // theta from scratch (pairs of units), then z = exp(-2 theta); padded units carry z = 0
+  auto refresh = [&]() {
+    const V *cW = reinterpret_cast<const V *>(net.W);
+    const V *cb = reinterpret_cast<const V *>(net.b);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int j0 = 2 * L * p + lane, j1 = j0 + L;
+      const V b0 = (cb && j0 < M) ? cb[j0] : P::mk(0.0f, 0.0f);
+      const V b1 = (cb && j1 < M) ? cb[j1] : P::mk(0.0f, 0.0f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        Zr[c][p] = P::mk(b0.x, b1.x);
+        Zi[c][p] = P::mk(b0.y, b1.y);
+      }
+    }
+    for (int i = 0; i < N; ++i) {
+      V xx[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float xv = ((sigx[c * W32 + (i >> 5)] >> (i & 31)) & 1u) ? s1 : s0;
+        xx[c] = P::mk(xv, xv);
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + lane, j1 = j0 + L;
+        const V w0 = (j0 < M) ? __ldg(cW + (int64_t)i * M + j0) : P::mk(0.0f, 0.0f);
+        const V w1 = (j1 < M) ? __ldg(cW + (int64_t)i * M + j1) : P::mk(0.0f, 0.0f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          Zr[c][p] = P::fma(xx[c], P::mk(w0.x, w1.x), Zr[c][p]);
+          Zi[c][p] = P::fma(xx[c], P::mk(w0.y, w1.y), Zi[c][p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int j0 = 2 * L * p + lane, j1 = j0 + L;
+        float e0 = exp_(-2.0f * Zr[c][p].x), e1 = exp_(-2.0f * Zr[c][p].y);
+        float sn0, cs0, sn1, cs1;
+        sincos_(-2.0f * Zi[c][p].x, &sn0, &cs0);
+        sincos_(-2.0f * Zi[c][p].y, &sn1, &cs1);
+        if (j0 >= M) e0 = 0.0f;
+        if (j1 >= M) e1 = 0.0f;
+        Zr[c][p] = P::mk(e0 * cs0, e1 * cs1);
+        Zi[c][p] = P::mk(e0 * sn0, e1 * sn1);
+      }
+      float acc = 0.0f;
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq) {
+        V prod = one;
+#pragma unroll
+        for (int p = gq * GL; p < (gq + 1) * GL && p < NP; ++p) {
+          const V aa = add2_(Zr[c][p], one);
+          V m = P::mul(aa, aa);
+          m = P::fma(Zi[c][p], Zi[c][p], m);
+          prod = P::mul(prod, m);
+        }
+        acc += P::lg2(prod.x * prod.y);
+      }
+      nlg[c] = fmaf(acc, -LEAN_FX, 32.0f);
+    }
+  };
+
+  // one Metropolis step of the C chains: table entry `e` (this step), rows at `slot` (lane offset applied), log2 u at
+  // s_tu[.][tb]
+  auto step = [&](const int4 e, const float *slot, const int tb) {
+    const uint32_t msk = (uint32_t)e.y;
+    uint32_t word[C];
+    bool up[C];
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      word[c] = *reinterpret_cast<volatile uint32_t *>(reinterpret_cast<volatile char *>(sigx + c * W32) + e.x);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      up[c] = (word[c] & msk) != 0u;
+      acc[c] = multiply(Zr[c], Zi[c], slot + (up[c] ? ROW : 0), true);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      // accept iff sum over lanes of 2^20 (log2|1+z'|^2 - log2|1+z|^2) > 2^20 (log2 u - (+-A_site))
+      int v = __float2int_rn(fmaf(acc[c], LEAN_FX, nlg[c])) >> 6;
+      const int thr = s_tu[c * SB + tb] - (up[c] ? -e.z : e.z);
+      if (lane == 0) v -= thr;
+      if (__reduce_add_sync(0xffffffffu, v) > 0) {
+        nlg[c] = fmaf(acc[c], -LEAN_FX, 32.0f);
+        ++n_acc;
+        *reinterpret_cast<volatile uint32_t *>(reinterpret_cast<volatile char *>(sigx + c * W32) + e.x) = word[c] ^ msk;
+      } else {
+        // rejected: multiply back by the other row of the slot (the inverse of the one just applied)
+        multiply(Zr[c], Zi[c], slot + (up[c] ? 0 : ROW), false);
+      }
+    }
+  };
+
+  // ---- prologue: rows of the first two chunks, random numbers of the first batch
+  const uint32_t q0 = phase >> LEAN_TSH;
+  issue_rows(q0);
+  cp_async_wait_all();
+  __syncthreads();
+  issue_rows(q0 + 1);
+  refill(0);
+
+  const float *lane_rows = rows + 4 * lane;
+  bool need_refresh = true;             // z is (re)computed from the configuration at the top of a chunk
+  uint32_t s = 0;                       // steps done
+  int left = a.sweep_size;              // steps left in the current sweep
+  int sweep = 0;
+  for (uint32_t q = q0; s < n_steps; ++q) {
+    const uint32_t pos_q = q << LEAN_TSH;                    // position of the chunk's first slot
+    if ((pos_q & (SB - 1)) == 0 && q != q0) refill(pos_q);
+    if (need_refresh) {
+      refresh();
+      need_refresh = false;
+    }
+    const float *cbase = lane_rows + (size_t)((q & 1u) << LEAN_TSH) * (2 * ROW);
+    const int4 *tbase = steptab + ((q & 1u) << LEAN_TSH);
+    const int tb0 = (int)(pos_q & (SB - 1));
+    const bool whole = pos_q >= phase && (uint64_t)pos_q - phase + T <= n_steps && left >= T;
+    if (whole) {
+#pragma unroll UNR
+      for (int tt = 0; tt < T; ++tt) step(tbase[tt], cbase + tt * (2 * ROW), tb0 + tt);
+      s += T;
+      left -= T;
+    } else {
+      for (int tt = 0; tt < T; ++tt) {
+        const int64_t sidx = (int64_t)pos_q + tt - (int64_t)phase;
+        if (sidx < 0 || sidx >= (int64_t)n_steps) continue;
+        step(tbase[tt], cbase + tt * (2 * ROW), tb0 + tt);
+        ++s;
+        if (--left == 0 && tt != T - 1) {
+          // sweep boundary inside the chunk: emit the configurations
+          left = a.sweep_size;
+          if (sweep >= a.n_discard && lane < W32) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+              if (c < n_valid)
+                a.samples[((chain0 + c) * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sigx[c * W32 + lane];
+          }
+          ++sweep;
+          if ((sweep % RATIO_REFRESH) == 0) need_refresh = true;
+        }
+      }
+    }
+    if (left == 0) {
+      left = a.sweep_size;
+      if (sweep >= a.n_discard && lane < W32) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (c < n_valid)
+            a.samples[((chain0 + c) * a.chain_length + (sweep - a.n_discard)) * W32 + lane] = sigx[c * W32 + lane];
+      }
+      ++sweep;
+      if ((sweep % RATIO_REFRESH) == 0) need_refresh = true;
+    }
+    // end of a chunk: the next one has landed everywhere, this one is free for the one after it
+    cp_async_wait_all();
+    __syncthreads();
+    issue_rows(q + 2);
+  }
+  cp_async_wait_all();
+  if (lane < W32) {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (c < n_valid) a.chain_state[(chain0 + c) * W32 + lane] = sigx[c * W32 + lane];
+  }
+  if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
+}
+
+template <int NP, int C, int GL, int UNR = 4>
+static int launch_ratio_lean(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
+                             const int *site_seq, const float *a0_seq, cudaStream_t st) {
+  constexpr int W = 16;
+  const size_t smem = lean_smem_bytes(NP, C, W, (net->n_visible + 31) >> 5);
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_kernel<NP, C, GL, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem);
+  if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
+  const int64_t blocks = (a.n_chains + (int64_t)C * W - 1) / ((int64_t)C * W);
+  sample_ratio_lean_kernel<NP, C, GL, UNR><<<(unsigned)blocks, W * 32, smem, st>>>(
+      make_netdev<float>(net), (const float *)ws, (float)a.s0, (float)a.s1, a, site_seq, a0_seq);
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
+}
+
+}  // namespace nkfb

@@ -766,8 +766,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <typename R, int NP, int C, int GL, int MAXW, int MINB>
 __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDev<R> net, const R *ws, const R s0, const R s1,
                                                                    SampArgs a, const int *site_seq, const R *a0_seq,
-                                                                   const int TSH, const int cta_chains,
-                                                                   const int short_mode) {
+                                                                   const int TSH) {
   using P = P2<R>;
   using V = typename P::V;
   using D = WarpDecide<R>;
@@ -786,21 +785,11 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
   // configurations of this warp's chains: [C][W32] words in shared memory (read with a broadcast LDS, flipped by
   // lane 0), which keeps 4 C registers free for a third chain per warp and lifts the N <= 128 limit
   uint32_t *sigx = reinterpret_cast<uint32_t *>(rows + (size_t)4 * T * ROW + (size_t)W * C * SB) + warp * C * W32;
-  // A CTA carries cta_chains <= C W chains.  When that is fewer than C W, n_short = C W - cta_chains warps run one
-  // chain short, chosen so that every SM sub-partition carries the same number of chains (a launch whose chains do
-  // not fill whole CTAs is bound by the busiest sub-partition: 16-warp CTAs with 28 chains = 7 per sub-partition
-  // step 12 % faster than full ones, while 14-warp CTAs are NOT spread 4/4/3/3 by the hardware and step 20 % slower).
-  // short_mode 0: the last n_short warps; 1: the warps with warp % 4 == 3.
-  const int n_short = C * W - cta_chains;
-  const bool is_short = short_mode == 0 ? (warp >= W - n_short) : ((warp & 3) == 3 && (warp >> 2) < n_short);
-  const int shorts_before = short_mode == 0 ? (warp > W - n_short ? warp - (W - n_short) : 0)
-                                            : ((warp >> 2) < n_short ? (warp >> 2) : n_short);
-  const int64_t chain0 = (int64_t)blockIdx.x * cta_chains + warp * C - shorts_before;
+  const int64_t chain0 = ((int64_t)blockIdx.x * W + warp) * C;
   const R *Qg = ws;  // global tables
   const V one = P::mk(R(1), R(1));
-  // chains of this warp that exist (a warp without chains still takes part in the CTA barriers and the row staging)
-  const int n_mine = C - (is_short ? 1 : 0);
-  const int n_valid = a.n_chains - chain0 >= n_mine ? n_mine : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
+  // chains of this warp that exist (the others are carried along: every warp takes part in the CTA barriers)
+  const int n_valid = a.n_chains - chain0 >= C ? C : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
 
   // ---- configurations
   for (int idx = lane; idx < C * W32; idx += 32) {
@@ -1002,15 +991,13 @@ __global__ void __launch_bounds__(32 * MAXW, MINB) sample_ratio_cta_kernel(NetDe
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         bit[c] = (word[c] >> (site & 31)) & 1u;
-        lgn[c] = R(0);
-        if (c < n_valid) lgn[c] = multiply(Zr[c], Zi[c], slot + bit[c] * ROW, true);
+        lgn[c] = multiply(Zr[c], Zi[c], slot + bit[c] * ROW, true);
         if (C > 2) asm volatile("" ::: "memory");  // keep the row loads of the next chain behind this one (registers)
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        if (c >= n_valid) continue;  // warp-uniform: an empty chain slot costs nothing
         const typename D::T thr = D::threshold(s_lu[c * SB + tb] - (bit[c] ? -a0 : a0));
-        if (D::accept(lgn[c] - lg[c], thr)) {
+        if (D::accept(lgn[c] - lg[c], thr) && c < n_valid) {
           lg[c] = lgn[c];
           ++n_acc;
           if (lane == 0) sigx[c * W32 + wsel] = word[c] ^ msk;
@@ -1064,8 +1051,7 @@ inline size_t ratio_cta_smem(int NP, int C, int W, int TSH, int W32) {
 
 template <typename R, int NP, int C, int GL, int MAXW = 16, int MINB = 1>
 static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
-                            const int *site_seq, const R *a0_seq, cudaStream_t st, int force_w = 0,
-                            int cta_chains_hint = 0) {
+                            const int *site_seq, const R *a0_seq, cudaStream_t st, int force_w = 0) {
   int W, TSH;
   ratio_cta_shape(a.n_chains, C, h->sm_count, MAXW, &W, &TSH);
   if (force_w > 0) {  // the launch shares the GPU with others: fewer, full CTAs instead of one CTA on every SM
@@ -1078,15 +1064,9 @@ static int launch_ratio_cta(nkfb_handle_t h, const nkfb_rbm_t *net, const SampAr
   cudaError_t rc = cudaFuncSetAttribute(sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
-  int cta_chains = C * W, short_mode = 0;
-  if (cta_chains_hint > 0 && cta_chains_hint < C * W && C * W - cta_chains_hint <= W) cta_chains = cta_chains_hint;
-  if (const char *e = getenv("NKFB_CTA_CHAINS")) cta_chains = atoi(e);  // tuning overrides
-  if (const char *e = getenv("NKFB_CTA_SHORT")) short_mode = atoi(e);
-  if (cta_chains < C * W - W || cta_chains > C * W || (short_mode == 1 && C * W - cta_chains > W / 4))
-    NKFB_FAIL(h, NKFB_ERR_INVALID, "bad chains-per-CTA %d for %d warps of %d chains", cta_chains, W, C);
-  const int64_t blocks = (a.n_chains + cta_chains - 1) / cta_chains;
+  const int64_t blocks = (a.n_chains + (int64_t)C * W - 1) / ((int64_t)C * W);
   sample_ratio_cta_kernel<R, NP, C, GL, MAXW, MINB><<<(unsigned)blocks, W * 32, smem, st>>>(
-      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a, site_seq, a0_seq, TSH, cta_chains, short_mode);
+      make_netdev<R>(net), (const R *)ws, (R)a.s0, (R)a.s1, a, site_seq, a0_seq, TSH);
   NKFB_LAUNCHED(h);
   return NKFB_OK;
 }

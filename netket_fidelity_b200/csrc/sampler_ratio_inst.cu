@@ -4,6 +4,9 @@
 #include <cstdlib>
 
 #include "sampler_ratio.cuh"
+#if NKFB_L == 32
+#include "sampler_lean.cuh"
+#endif
 
 namespace nkfb {
 
@@ -96,8 +99,18 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
       SampArgs ah = a;
       ah.n_chains = head;
       const int fw = w16 ? 16 : 0;
-      int rc = gl_one ? launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw)
-                      : launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw);
+      int rc;
+      bool lean = false;
+      if constexpr (sizeof(NKFB_RT) == 4 && CC == 2) lean = !getenv("NKFB_NOLEAN");
+      if constexpr (sizeof(NKFB_RT) == 4 && CC == 2) {
+        // single precision, two chains per warp: the lean form of the CTA-synchronous kernel (sampler_lean.cuh)
+        if (lean)
+          rc = gl_one ? launch_ratio_lean<NP, 2, 1>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st)
+                      : launch_ratio_lean<NP, 2, GW>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st);
+      }
+      if (!lean)
+        rc = gl_one ? launch_ratio_cta<NKFB_RT, NP, CC, 1>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw)
+                    : launch_ratio_cta<NKFB_RT, NP, CC, GW>(h, net, ah, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st, fw);
       if (rc || head == a.n_chains) return rc;
       const int W32 = (net->n_visible + 31) >> 5;
       SampArgs at = a;
@@ -169,6 +182,15 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
       case 41: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 10, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 42: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 16, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 43: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 8, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 50: return launch_ratio_lean<7, 2, 4, 8>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 51: return launch_ratio_lean<7, 2, 4, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 52: return launch_ratio_lean<7, 2, 4, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 53: return launch_ratio_lean<7, 2, 4, 1>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 54: return launch_ratio_lean<7, 2, 7, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 44: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 45: return launch_ratio_cta<NKFB_RT, 7, 1, 2, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 46: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 24, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
+      case 47: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 28, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 34: return launch_ratio_cta<NKFB_RT, 7, 3, 4, 12>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 35: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 8>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 36: return launch_ratio_cta<NKFB_RT, 7, 4, 4, 10>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);

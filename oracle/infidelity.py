@@ -103,9 +103,10 @@ def infidelity_and_grad(psi, phi, sigma, eta, cv_coeff=None, U1=None, U2=None, U
     t_e = np.conj(np.tanh(th_e))                       # (S,C,M)
     we = w_eta[:, None] * np.conj(rho2)                # (S,C)
     ye = we[:, :, None] * t_e                          # (S,C,M)
-    gW = gW + np.einsum("sci,scj->ij", xp2.astype(np.complex128), ye)
+    xc = xp2.reshape(S * C, N).astype(np.complex128)   # sum over (s, c) as one matrix product (BLAS)
+    gW = gW + xc.T @ ye.reshape(S * C, -1)
     gb = gb + ye.sum(axis=(0, 1))
-    ga = ga + np.einsum("sci,sc->i", xp2.astype(np.complex128), we)
+    ga = ga + xc.T @ we.reshape(S * C)
 
     gW, gb, ga = -gW / S, -gb / S, -ga / S
     if not np.issubdtype(psi.dtype, np.complexfloating):
