@@ -31,12 +31,32 @@ constexpr int LEAN_SB = 128;                  // steps per RNG batch
 constexpr float LEAN_FX = 67108864.0f;        // 2^26: fixed point of the addend inside F2I; >> 6 afterwards
 constexpr float LEAN_FT = 1048576.0f;         // 2^20: fixed point of the thresholds
 
+// z <- z q on a pair of units, ONE asm statement whose outputs are tied to the registers of z: the accept path of the
+// step then has nothing to copy (with separate statements ptxas kept the new z of some pairs in temporaries and
+// paid a dozen MOVs per accepted move)
+__device__ __forceinline__ void lean_cmul(float2 &zr, float2 &zi, const float2 ql, const float2 qh) {
+  unsigned long long &ZR = reinterpret_cast<unsigned long long &>(zr), &ZI = reinterpret_cast<unsigned long long &>(zi);
+  asm("{\n\t.reg .b64 s, t, nt;\n\t.reg .f32 t0, t1;\n\t"
+      "mul.rn.f32x2 s, %0, %3;\n\t"
+      "mul.rn.f32x2 t, %1, %3;\n\t"
+      "mov.b64 {t0, t1}, t;\n\t"
+      "neg.f32 t0, t0;\n\t"
+      "neg.f32 t1, t1;\n\t"
+      "mov.b64 nt, {t0, t1};\n\t"
+      "fma.rn.f32x2 %1, %1, %2, s;\n\t"
+      "fma.rn.f32x2 %0, %0, %2, nt;\n\t}"
+      : "+l"(ZR), "+l"(ZI)
+      : "l"(reinterpret_cast<const unsigned long long &>(ql)), "l"(reinterpret_cast<const unsigned long long &>(qh)));
+}
+
 inline size_t lean_smem_bytes(int NP, int C, int W, int W32) {
   return (size_t)4 * LEAN_T * 4 * NP * 32 * 4 + (size_t)2 * LEAN_T * 16 + (size_t)W * C * LEAN_SB * 4 + (size_t)W * C * W32 * 4;
 }
 
-template <int NP, int C, int GL, int UNR>
-__global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float> net, const float *ws, const float s0,
+// NP pairs of units per lane; C chains per warp; GL pairs per logarithm; UNR unroll factor of the steps of a chunk;
+// W_ warps per CTA; SG pairs whose row entries are in registers at a time
+template <int NP, int C, int GL, int UNR, int W_, int SG>
+__global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_kernel(NetDev<float> net, const float *ws, const float s0,
                                                                    const float s1, SampArgs a, const int *site_seq,
                                                                    const float *a0_seq) {
   using P = P2<float>;
@@ -109,7 +129,8 @@ __global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float>
       const int st = __ldg(site_seq + sc);
       const char *src = reinterpret_cast<const char *>(ws + (size_t)(tab * N + st) * ROW);
       char *dst = reinterpret_cast<char *>(rows + ((((qn & 1u) << LEAN_TSH) + tt) * 2 + tab) * ROW);
-      for (int off = lane * 16; off < (int)(ROW * sizeof(float)); off += 512) cp_async16(dst + off, src + off);
+#pragma unroll
+      for (int k = 0; k < NP; ++k) cp_async16(dst + lane * 16 + k * 512, src + lane * 16 + k * 512);  // ROW = 512 NP bytes
     }
     if (threadIdx.x < T) {
       const int tt = threadIdx.x;
@@ -127,41 +148,53 @@ __global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float>
 
   // z <- z * row (in place); returns this lane's sum_j log2 |1 + z_j|^2.  rp: shared memory, lane offset applied.
   auto multiply = [&](V (&zr)[NP], V (&zi)[NP], const float *rp, bool want_log) -> float {
+    // SG pairs at a time (row loads, complex multiply, |1 + z|^2), one logarithm per GL pairs
     float acc = 0.0f;
 #pragma unroll
     for (int gq = 0; gq < NG; ++gq) {
-      constexpr int GS = GL;
-      V qlo[GS], qhi[GS], m[GS];
+      V prod = one;
 #pragma unroll
-      for (int i = 0; i < GS; ++i) {
-        const int p = gq * GL + i;
-        if (p < NP) {
-          const float4 q = *reinterpret_cast<const float4 *>(rp + 4 * L * p);
-          qlo[i] = make_float2(q.x, q.y);
-          qhi[i] = make_float2(q.z, q.w);
+      for (int sq = 0; sq < GL; sq += SG) {
+        V qlo[SG], qhi[SG], m[SG];
+#pragma unroll
+        for (int i = 0; i < SG; ++i) {
+          const int p = gq * GL + sq + i;
+          if (sq + i < GL && p < NP) {
+            const float4 q = *reinterpret_cast<const float4 *>(rp + 4 * L * p);
+            qlo[i] = make_float2(q.x, q.y);
+            qhi[i] = make_float2(q.z, q.w);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < SG; ++i) {
+          const int p = gq * GL + sq + i;
+          if (sq + i < GL && p < NP) lean_cmul(zr[p], zi[p], qlo[i], qhi[i]);
+        }
+        if (want_log) {
+#pragma unroll
+          for (int i = 0; i < SG; ++i) {
+            const int p = gq * GL + sq + i;
+            if (sq + i < GL && p < NP) m[i] = add2_(zr[p], one);
+          }
+#pragma unroll
+          for (int i = 0; i < SG; ++i) {
+            const int p = gq * GL + sq + i;
+            if (sq + i < GL && p < NP) m[i] = P::mul(m[i], m[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < SG; ++i) {
+            const int p = gq * GL + sq + i;
+            if (sq + i < GL && p < NP) m[i] = P::fma(zi[p], zi[p], m[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < SG; ++i) {
+            const int p = gq * GL + sq + i;
+            if (sq + i < GL && p < NP) prod = (sq + i == 0) ? m[i] : P::mul(prod, m[i]);
+          }
         }
       }
-#pragma unroll
-      for (int i = 0; i < GS; ++i) {
-        const int p = gq * GL + i;
-        if (p < NP) cmul_inplace(zr[p], zi[p], qlo[i], qhi[i]);
-      }
       if (want_log) {
-#pragma unroll
-        for (int i = 0; i < GS; ++i)
-          if (gq * GL + i < NP) m[i] = add2_(zr[gq * GL + i], one);
-#pragma unroll
-        for (int i = 0; i < GS; ++i)
-          if (gq * GL + i < NP) m[i] = P::mul(m[i], m[i]);
-#pragma unroll
-        for (int i = 0; i < GS; ++i)
-          if (gq * GL + i < NP) m[i] = P::fma(zi[gq * GL + i], zi[gq * GL + i], m[i]);
-#pragma unroll
-        for (int st = 1; st < GS; st <<= 1)
-#pragma unroll
-          for (int i = 0; i < GS; ++i)
-            if (i % (2 * st) == 0 && i + st < GS && gq * GL + i + st < NP) m[i] = P::mul(m[i], m[i + st]);
-        const float lv = P::lg2(m[0].x * m[0].y);
+        const float lv = P::lg2(prod.x * prod.y);
         acc = gq == 0 ? lv : acc + lv;
       }
     }
@@ -254,7 +287,7 @@ __global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float>
       int v = __float2int_rn(fmaf(acc[c], LEAN_FX, nlg[c])) >> 6;
       const int thr = s_tu[c * SB + tb] - (up[c] ? -e.z : e.z);
       if (lane == 0) v -= thr;
-      if (__reduce_add_sync(0xffffffffu, v) > 0) {
+      if (__builtin_expect(__reduce_add_sync(0xffffffffu, v) > 0, 1)) {
         nlg[c] = fmaf(acc[c], -LEAN_FX, 32.0f);
         ++n_acc;
         *reinterpret_cast<volatile uint32_t *>(reinterpret_cast<volatile char *>(sigx + c * W32) + e.x) = word[c] ^ msk;
@@ -339,16 +372,16 @@ __global__ void __launch_bounds__(512, 1) sample_ratio_lean_kernel(NetDev<float>
   if (a.n_accepted && lane == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-template <int NP, int C, int GL, int UNR = 4>
+template <int NP, int C, int GL, int UNR = 8, int W_ = 16, int SG = 2>
 static int launch_ratio_lean(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws,
                              const int *site_seq, const float *a0_seq, cudaStream_t st) {
-  constexpr int W = 16;
+  constexpr int W = W_;
   const size_t smem = lean_smem_bytes(NP, C, W, (net->n_visible + 31) >> 5);
-  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_kernel<NP, C, GL, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_kernel<NP, C, GL, UNR, W_, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   const int64_t blocks = (a.n_chains + (int64_t)C * W - 1) / ((int64_t)C * W);
-  sample_ratio_lean_kernel<NP, C, GL, UNR><<<(unsigned)blocks, W * 32, smem, st>>>(
+  sample_ratio_lean_kernel<NP, C, GL, UNR, W_, SG><<<(unsigned)blocks, W * 32, smem, st>>>(
       make_netdev<float>(net), (const float *)ws, (float)a.s0, (float)a.s1, a, site_seq, a0_seq);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

@@ -182,11 +182,12 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
       case 41: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 10, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 42: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 16, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 43: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 8, 3>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
-      case 50: return launch_ratio_lean<7, 2, 4, 8>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
-      case 51: return launch_ratio_lean<7, 2, 4, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
-      case 52: return launch_ratio_lean<7, 2, 4, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
-      case 53: return launch_ratio_lean<7, 2, 4, 1>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
-      case 54: return launch_ratio_lean<7, 2, 7, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 50: return launch_ratio_lean<7, 2, 4, 8, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 51: return launch_ratio_lean<7, 2, 4, 8, 16, 1>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 52: return launch_ratio_lean<7, 2, 4, 8, 16, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 53: return launch_ratio_lean<7, 2, 4, 4, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 54: return launch_ratio_lean<7, 2, 7, 8, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 55: return launch_ratio_lean<7, 2, 7, 8, 16, 1>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
       case 44: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 45: return launch_ratio_cta<NKFB_RT, 7, 1, 2, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 46: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 24, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);

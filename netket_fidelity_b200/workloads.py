@@ -18,6 +18,8 @@ def make_workload(name):
                     U=("ising_prop", 0.01, 1.0, 1.0), vb=True)
     if name == "C4":   # north star: 10x10, alpha=4, 2^20 sample pairs
         return dict(N=100, M=400, n_chains=16384, chain_length=64, mode="upsi", U=("rx", 0, 0.1), vb=True)
+    if name == "C5":   # Renyi-2 swap estimator on an 8x8 lattice, subsystem = half of the system, no gradient
+        return dict(N=64, M=128, n_chains=16384, chain_length=64, mode="renyi2", partition=tuple(range(32)), vb=True)
     raise ValueError(name)
 
 
