@@ -200,6 +200,16 @@ int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *
 int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums,
                        int64_t P, int dtype, void *grad_out, void *stream);
 
+/* One-collective form of the step (reference: ONE mean over ranks, overlap/expect.py:126).
+ * acc1 = the pass-B accumulator obtained by handing nkfb_infidelity_grad `centre_sums` = {c0 n, ., ., ., n, ...} in
+ * place of the all-reduced sums (any centring constant c0 that is identical on all ranks, e.g. the previous step's F),
+ * so that pass B does not have to wait for the global mean; acc2 = sum_s conj O_k(sigma_s) (nkfb_weighted_score with
+ * unit weights).  After ONE all-reduce over [sums | acc1 | acc2]:
+ * grad_out = -(acc1 + 2 (c0 - F) acc2) / n, F = sums[0] / sums[4] -- exact algebra, not an approximation.
+ * All pointers are device pointers. */
+int nkfb_grad_finalize_centred(nkfb_handle_t h, const double *acc1, const double *acc2, const double *sums,
+                               const double *centre_sums, int64_t P, int dtype, void *grad_out, void *stream);
+
 /* ---- chain statistics ---------------------------------------------------- */
 /* Partial sums needed by nk.stats.statistics on data viewed as (rows, cols):
  * per row: [sum, sum of first half, sum of second half] and `n_blocks` block sums of
@@ -230,6 +240,15 @@ int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void *params, co
                           int64_t t, int real_params, void *stream);
 
 /* ---- MUFU / FP32 micro-benchmarks (roofline denominators) ---------------- */
+/* Jacobian-vector product u_s = sum_k O_k(x_s) v_k of the RBM log-amplitude over a batch (O_k = d log psi / d theta_k;
+ * `vec` = P complex numbers of the net's dtype in the flat parameter layout [bias (M) | kernel (N x M) | visible_bias
+ * (N)], `out` = S complex numbers).  With nkfb_weighted_score (sum_s w_s conj O_k(x_s)) it gives the action of the
+ * quantum geometric tensor S v = <O^* (O v)> - <O^*><O v> without ever forming O: the stochastic-reconfiguration
+ * preconditioner behind `preconditioner=` of the reference driver (driver/infidelity_optimizer.py:40,148,205-233;
+ * NetKet nk.optimizer.SR / QGTOnTheFly). */
+int nkfb_score_dot(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_t *packed, int64_t S,
+                   const double local_states[2], const void *vec, void *out, void *stream);
+
 /* Pipe-rate micro-benchmarks behind the roofline denominators bench.py reports (MEASURED_PEAKS.json holds only the
  * HBM and bf16 tensor peaks): `iters` rounds of 8 independent chains per thread on a full grid of
  * kind 0 MUFU.EX2, 1 MUFU.COS, 2 MUFU.LG2, 3 FFMA with immediate operands, 4 FFMA with three register operands,

@@ -23,6 +23,7 @@ SYMBOLS = [
     "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample", "nkfb_sample_workspace_bytes",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
     "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update", "nkfb_set_option", "nkfb_weighted_score",
+    "nkfb_score_dot", "nkfb_grad_finalize_centred",
 ]
 
 OPT_SAMPLER_ALGO = 1
@@ -95,6 +96,8 @@ def load_library():
         lib.nkfb_microbench.argtypes = [vp, i32, i32, P(dbl), vp]
         lib.nkfb_set_option.argtypes = [vp, i32, i64]
         lib.nkfb_weighted_score.argtypes = [vp, P(RbmT), vp, i64, P(dbl), vp, vp, vp]
+        lib.nkfb_grad_finalize_centred.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
+        lib.nkfb_score_dot.argtypes = [vp, P(RbmT), vp, i64, P(dbl), vp, vp, vp]
         lib.nkfb_optimizer_update.argtypes = [vp, i32, i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, i64, i32, vp]
         for name in SYMBOLS:
             getattr(lib, name)  # AttributeError if the ABI drifted
@@ -374,10 +377,29 @@ class Handle:
                                                  _ptr(weights), _ptr(acc), self._stream()), "nkfb_weighted_score")
         return acc
 
+    def score_dot(self, net: RbmSpec, packed, local_states, vec):
+        """u_s = sum_k O_k(x_s) v_k; vec (P,) complex in the flat parameter layout, returns (S,) complex."""
+        S = packed.shape[0]
+        self._on_device(net.kernel, packed, vec)
+        vec = vec.to(complex_dtype(net.code)).contiguous()
+        out = torch.empty((S,), dtype=complex_dtype(net.code), device=packed.device)
+        ns = net.struct()
+        self._check(self.lib.nkfb_score_dot(self.h, C.byref(ns), _ptr(packed), S, _ls(local_states), _ptr(vec),
+                                            _ptr(out), self._stream()), "nkfb_score_dot")
+        return out
+
     def grad_finalize(self, grad_acc, sums, P, dtype):
         out = torch.empty((P,), dtype=dtype, device=grad_acc.device)
         self._check(self.lib.nkfb_grad_finalize(self.h, _ptr(grad_acc), _ptr(sums), P, real_dtype_code(dtype),
                                                 _ptr(out), self._stream()), "nkfb_grad_finalize")
+        return out
+
+    def grad_finalize_centred(self, acc1, acc2, sums, centre_sums, P, dtype):
+        """I_grad = -(acc1 + 2 (c0 - F) acc2) / n, c0 = centre_sums[0] / centre_sums[4] (one-collective step)."""
+        out = torch.empty((P,), dtype=dtype, device=acc1.device)
+        self._check(self.lib.nkfb_grad_finalize_centred(self.h, _ptr(acc1), _ptr(acc2), _ptr(sums), _ptr(centre_sums), P,
+                                                        real_dtype_code(dtype), _ptr(out), self._stream()),
+                    "nkfb_grad_finalize_centred")
         return out
 
     # ---------------------------------------------------------------- statistics

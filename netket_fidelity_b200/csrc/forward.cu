@@ -648,7 +648,8 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
                       cudaStream_t st);
 int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
                        const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
-                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st);
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st,
+                       const void *weights = nullptr);
 }
 
 extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
@@ -733,11 +734,51 @@ extern "C" int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const
   if (S <= 0) return NKFB_OK;
   if (!packed || !weights || !acc) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // tensor-core path (single precision, S >= 2048): the sigma side of pass B with the given weights
+    const char *impl = getenv("NKFB_GRAD_IMPL");
+    if (!(impl && strcmp(impl, "simt") == 0)) {
+      rc = tc_infidelity_grad(h, net, nullptr, packed, packed, S, local_states, NAN, nullptr, nullptr, nullptr, acc, st,
+                              weights);
+      if (rc <= 0) return rc;
+    }
+  }
   if (net->dtype == NKFB_F32)
     return launch_grad<float, 8>(h, net, nullptr, packed, packed, S, local_states, NAN, nullptr, nullptr, nullptr, acc,
                                  st, weights);
   return launch_grad<double, 4>(h, net, nullptr, packed, packed, S, local_states, NAN, nullptr, nullptr, nullptr, acc,
                                 st, weights);
+}
+
+namespace nkfb {
+// one-collective form: acc1 was accumulated with the centring constant c0 instead of the global mean F,
+// acc2 = sum_s conj O_k(sigma_s); I_grad = -(acc1 + 2 (c0 - F) acc2) / n with F = sums[0] / sums[4] AFTER the all-reduce
+template <typename R>
+__global__ void grad_finalize_centred_kernel(const double *acc1, const double *acc2, const double *sums,
+                                             const double *centre, int64_t n2, R *out) {
+  const double n = sums[4], F = sums[0] / n, c0 = centre[0] / centre[4];
+  const double k = 2.0 * (c0 - F);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (R)(-(acc1[i] + k * acc2[i]) / n);
+}
+}  // namespace nkfb
+
+extern "C" int nkfb_grad_finalize_centred(nkfb_handle_t h, const double *acc1, const double *acc2, const double *sums,
+                                          const double *centre_sums, int64_t P, int dtype, void *grad_out,
+                                          void *stream) {
+  if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
+  if (!acc1 || !acc2 || !sums || !centre_sums || !grad_out || P <= 0) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad finalize arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)std::min<int64_t>((2 * P + 255) / 256, 1024);
+  if (dtype == NKFB_F32)
+    grad_finalize_centred_kernel<float><<<grid, 256, 0, st>>>(acc1, acc2, sums, centre_sums, 2 * P, (float *)grad_out);
+  else if (dtype == NKFB_F64)
+    grad_finalize_centred_kernel<double><<<grid, 256, 0, st>>>(acc1, acc2, sums, centre_sums, 2 * P, (double *)grad_out);
+  else
+    NKFB_FAIL(h, NKFB_ERR_INVALID, "bad dtype");
+  NKFB_LAUNCHED(h);
+  return NKFB_OK;
 }
 
 extern "C" int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const double *sums, int64_t P, int dtype,

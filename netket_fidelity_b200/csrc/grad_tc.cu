@@ -29,6 +29,7 @@ struct TcGradArgs {
   TcGeom g;
   int64_t tiles_per_split;
   int has_bias, has_vbias;
+  const cx<float> *weights;  // weighted-score mode (nkfb_weighted_score): w_sig = weights[s], sigma side only
 };
 
 // tanh z with MUFU: sg ((1 - t^2) + 2 i t sin 2y) / (1 + 2 t cos 2y + t^2), t = e^{-2|x|}
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
   const bool gate = a.op2.kind == NKFB_OP_GATE;
   const int gidx = a.op2.idx;
   const float ssum = a.s0 + a.s1;
-  const double F = a.sums[0] / a.sums[4];
+  const double F = a.weights ? 0.0 : a.sums[0] / a.sums[4];
   const float cvc = a.has_cv ? a.cv : 0.f;
 
   if (tid == 0) {
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
     if (tid < TC_ROWS) {
       const int64_t gs = s_base + tid;
       cx<float> ws_ = mk<float>(0, 0), we_ = mk<float>(0, 0), rh_ = mk<float>(0, 0);
-      if (gs < a.S) {
+      if (gs < a.S && a.weights) {
+        ws_ = a.weights[gs];
+      } else if (gs < a.S) {
         const cx<float> A = cexp(a.log_val[gs]);
         const float A2 = abs2(A);
         const float Lv = A.re + cvc * (A2 - 1.f);
@@ -148,8 +151,9 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
       wts[TC_ROWS + tid] = we_;
       wts[2 * TC_ROWS + tid] = rh_;
     }
+    const int n_sides = a.weights ? 1 : 2;
 #pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
+    for (int side = 0; side < n_sides; ++side) {
       const uint32_t *packed = side == 0 ? a.sigma : a.eta;
       const bool flip = gate && side == 1;
       tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, true, xtab);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
 // returns NKFB_OK, an error, or 1 when the tensor-core path does not apply
 int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
                        const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
-                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st) {
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st, const void *weights) {
   if (psi->dtype != NKFB_F32) return 1;
   if (op2 && op2->kind == NKFB_OP_ISING) return 1;
   if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
@@ -340,6 +344,7 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   a.log_val = (const cx<float> *)log_val;
   a.rho1 = (const cx<float> *)rho1;
   a.sums = sums;
+  a.weights = (const cx<float> *)weights;
   a.grad_acc = grad_acc;
   a.prep = (const __nv_bfloat16 *)h->ws3;
   a.g = g;

@@ -29,7 +29,7 @@ from . import parallel as par
 
 class StepConfig:
     def __init__(self, n_chains, chain_length, n_discard, sweep_size=None, seed=0, local_states=(-1.0, 1.0),
-                 cv_coeff=-0.5, site_mode=0):
+                 cv_coeff=-0.5, site_mode=0, one_collective=False):
         self.n_chains = int(n_chains)            # GLOBAL number of chains per family
         self.chain_length = int(chain_length)
         self.n_discard = int(n_discard)
@@ -38,6 +38,9 @@ class StepConfig:
         self.local_states = tuple(local_states)
         self.cv_coeff = cv_coeff
         self.site_mode = site_mode
+        # one all-reduce per step instead of two: pass B is centred with the PREVIOUS step's F and an
+        # extra accumulator sum_s conj O_k(sigma_s) makes the result exact; costs the sigma half of pass B once more
+        self.one_collective = bool(one_collective)
 
 
 class InfidelityStep:
@@ -82,6 +85,11 @@ class InfidelityStep:
         self.acc = torch.zeros((8 + 2 * P,), dtype=torch.float64, device=dev)
         self.sums = self.acc[:8]
         self.grad_acc = self.acc[8:]
+        if cfg.one_collective:
+            # [sums (8) | acc1 (2P) | acc2 (2P)]: the ONE buffer that crosses NVLink; centre = {c0 n_local, ..., n_local}
+            self.acc_one = torch.zeros((8 + 4 * P,), dtype=torch.float64, device=dev)
+            self.centre = torch.zeros((8,), dtype=torch.float64, device=dev)
+            self.ones_w = torch.ones((self.S_local,), dtype=cdtype, device=dev)
         self.n_accepted = torch.zeros((2,), dtype=torch.int64, device=dev)
         # the two chain families are sampled on two streams so that the tail of one launch (a partial last
         # wave of CTAs) overlaps the other launch; each has its own scratch for the pre-scaled parameters
@@ -141,6 +149,8 @@ class InfidelityStep:
         cfg = self.cfg
         sig = self.sigma.view(-1, self.W32)
         eta = self.eta.view(-1, self.W32)
+        if cfg.one_collective and return_grad:
+            return self._estimate_one_collective(psi, phi, sig, eta, events)
         self.acc.zero_()
         if events:
             events[0].record()
@@ -159,6 +169,32 @@ class InfidelityStep:
             grad = self.h.grad_finalize(self.grad_acc, self.sums, self.P, self.cdtype)
         self.last = dict(log_val=log_val, L=L, rho1=rho1)
         return self.sums, L, grad
+
+    def _estimate_one_collective(self, psi, phi, sig, eta, events=None):
+        """Pass A, pass B centred with the previous step's F, sum_s conj O_k(sigma_s), ONE all-reduce, finalize."""
+        cfg, P = self.cfg, self.P
+        buf = self.acc_one
+        buf.zero_()
+        sums, acc1, acc2 = buf[:8], buf[8:8 + 2 * P], buf[8 + 2 * P:]
+        if events:
+            events[0].record()
+        log_val, L, rho1, _ = self.h.infidelity_fwd(psi, phi, sig, eta, cfg.local_states, cfg.cv_coeff, self.op1,
+                                                    self.op2, self.op4, sums=sums)
+        if events:
+            events[1].record()
+        # centre[0] / centre[4] = c0 (kept on the device from the previous step; 0 before the first one)
+        self.centre[4] = float(self.S_local)
+        self.h.infidelity_grad(psi, sig, eta, cfg.local_states, cfg.cv_coeff, log_val, rho1, self.centre,
+                               op2=self.op2, grad_acc=acc1)
+        self.h.weighted_score(psi, sig, cfg.local_states, self.ones_w, acc=acc2)
+        if events:
+            events[2].record()
+        self._allreduce(buf)                                       # the one collective of the step
+        grad = self.h.grad_finalize_centred(acc1, acc2, sums, self.centre, P, self.cdtype)
+        self.centre[0] = sums[0] / sums[4] * float(self.S_local)   # next step's centring constant (device op)
+        self.last = dict(log_val=log_val, L=L, rho1=rho1)
+        self.sums = sums
+        return sums, L, grad
 
     def step(self, psi, phi, return_grad=True):
         """reset + sample both families + estimator (+ gradient): the unit bench.py times."""

@@ -166,3 +166,48 @@ def test_default_seed_is_broadcast_from_rank_zero():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, 1000, True), (1, 1000, True)]
+
+
+def _one_collective_worker(rank, world, port, q):
+    """SURVEY B.3 on two gloo ranks: every rank centres pass B with the SAME constant c0 (not the global mean),
+    accumulates v2 = sum_s conj O_k(sigma_s) beside it, ONE all-reduce over [sums | v1 | v2], and
+    grad = -(v1 + 2 (c0 - F) v2) / n equals the single-rank gradient exactly."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from netket_fidelity_b200 import parallel as par
+    N, S = 4, 64
+    psi, phi = RBMParams.random(N, 2, 1, std=0.2), RBMParams.random(N, 2, 2, std=0.2)
+    rng = np.random.default_rng(0)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    U, Ud, cv, c0 = oops.Rx(N, 1, 0.3), oops.Rx(N, 1, -0.3), -0.5, 0.37
+    sl = slice(rank * S // world, (rank + 1) * S // world)
+    lv, xp2, rho2 = local_log_val(psi, phi, sigma[sl], eta[sl], U, Ud, None)
+    A, L = np.exp(lv), local_estimator(lv, cv)
+    v1 = _local_pass_B(psi, sigma[sl], eta[sl], A, L, c0, cv, xp2, rho2)          # centred with c0, not with F
+    t = np.conj(np.tanh(rbm_theta(psi, sigma[sl])))
+    v2 = np.concatenate([t.sum(0), (sigma[sl].T.astype(complex) @ t).ravel(), sigma[sl].sum(0).astype(complex)])
+    buf = torch.cat([torch.tensor([L.sum(), (L ** 2).sum(), 0, 0, len(L), 0, 0, 0], dtype=torch.float64),
+                     torch.view_as_real(torch.tensor(v1)).reshape(-1), torch.view_as_real(torch.tensor(v2)).reshape(-1)])
+    par.allreduce_sum_(buf)                                                        # the one collective
+    P = v1.size
+    sums = buf[:8].numpy()
+    V1 = torch.view_as_complex(buf[8:8 + 2 * P].reshape(-1, 2)).numpy()
+    V2 = torch.view_as_complex(buf[8 + 2 * P:].reshape(-1, 2)).numpy()
+    F = sums[0] / sums[4]
+    grad = -(V1 + 2 * (c0 - F) * V2) / sums[4]
+    ref = infidelity_and_grad(psi, phi, sigma, eta, cv, U, Ud, None)
+    q.put((rank, bool(abs(F - ref["F"]) < 1e-13 and np.allclose(grad, ref["grad"].ravel(), rtol=1e-10, atol=1e-13))))
+    dist.destroy_process_group()
+
+
+def test_one_collective_algebra_on_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_one_collective_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
