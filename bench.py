@@ -388,20 +388,20 @@ def run_b200(args):
     infid = 1.0 - s[0] / s[4]
     acc_rate = eng.n_accepted.sum().item() / (2.0 * eng.local_chains * (5 + w["chain_length"]) * N * eng.steps_done)
     graph_ms = None
-    if args.graph and world == 1:
+    if args.graph:
         # the same K steps replayed from ONE captured CUDA graph per step (engine.capture_graph)
         eng.capture_graph(specs["psi"], specs["phi"])
         for _ in range(3):
             eng.step(specs["psi"], specs["phi"])
-        torch.cuda.synchronize()
+        ctx.barrier()
         g0, g1 = ctx.ev(), ctx.ev()
         g0.record()
         for i in range(args.steps):
             ctx.flush.zero_()
             eng.step(specs["psi"], specs["phi"])
         g1.record()
-        torch.cuda.synchronize()
-        graph_ms = g0.elapsed_time(g1) / args.steps
+        ctx.barrier()
+        graph_ms = ctx.max_over_ranks(g0.elapsed_time(g1)) / args.steps
     # clocks under load: samples that arrived during the timed region; when it is shorter than nvidia-smi's period
     # (multi-GPU runs: tens of ms) every rank keeps running the same step, untimed, until rank 0 has two samples
     t_wall1 = time.time()

@@ -164,7 +164,8 @@ int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op_t *op,
  *   L_s = Re e^{l_s} + cv (e^{2 Re l_s} - 1)          (cv = NaN <-> cv_coeff None)
  * Outputs (device): log_val (S) complex, L (S) real, rho1 (S) complex (weight of the
  * flipped connected element of op2, 0 if op2 is NONE), all of psi->dtype;
- * sums: double[8] ACCUMULATED: [sum L, sum L^2, sum |A|^2, sum Re A, S, 0, 0, 0]. */
+ * sums: double[8] ACCUMULATED: [sum L, sum L^2, sum |A|^2, sum Re A, S, n_bad, 0, 0]; n_bad counts the local
+ * estimators that came out NaN or infinite (a diverged network: the caller can stop instead of stepping on). */
 int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
                         const nkfb_op_t *op1, const nkfb_op_t *op2, const nkfb_op_t *op4,
                         const uint32_t *sigma, const uint32_t *eta, int64_t S,

@@ -320,6 +320,7 @@ extern "C" int nkfb_chain_stats(nkfb_handle_t h, const void *L, int dtype, int64
                                 int64_t l_block, int64_t n_blocks, double *out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_chain_stats");
   if (!L || !out || rows < 1 || cols < 1 || l_block < 1 || n_blocks < 0 || n_blocks * l_block > cols)
     NKFB_FAIL(h, NKFB_ERR_INVALID, "bad chain_stats arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -417,6 +418,7 @@ extern "C" int nkfb_optimizer_update(nkfb_handle_t h, int kind, int dtype, void 
                                      int real_params, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_optimizer_update");
   if (!params || !grad || P <= 0 || (kind == 1 && (!m || !v)) || t < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad optimizer arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const double c1 = 1.0 - pow(b1, (double)t), c2 = 1.0 - pow(b2, (double)t);

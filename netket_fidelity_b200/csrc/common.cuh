@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges around the entry points (no-ops without a profiler attached)
+
 #include "../../include/nkfb200.h"
 
 struct nkfb_handle_s {
@@ -36,6 +38,13 @@ struct NkfbDeviceGuard {
   }
 };
 #define NKFB_DEVICE_GUARD(h) NkfbDeviceGuard nkfb_device_guard__((h)->device)
+
+// NVTX range over one entry point (nsys / ncu --nvtx timelines: "nkfb_sample", "nkfb_infidelity_fwd", ...)
+struct NkfbNvtxRange {
+  explicit NkfbNvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NkfbNvtxRange() { nvtxRangePop(); }
+};
+#define NKFB_NVTX(name) NkfbNvtxRange nkfb_nvtx_range__(name)
 
 #define NKFB_CHECK_CUDA(h, call)                                                        \
   do {                                                                                  \

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT) infid_fwd_kernel(NetDev<R> psi, NetDev<R> 
     ops[3] = a.op4;
   }
   const R s0 = (R)a.s0, s1 = (R)a.s1;
-  double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0;
+  double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0, sbad = 0;  // sbad: local estimators that are NaN or infinite
   for (int64_t tile = blockIdx.x; tile * TS < a.S; tile += gridDim.x) {
     const int64_t s_base = tile * TS;
     __syncthreads();
@@ -126,12 +126,13 @@ __global__ void __launch_bounds__(NT) infid_fwd_kernel(NetDev<R> psi, NetDev<R> 
         sA2 += (double)A2;
         sRe += (double)A.re;
         sn += 1.0;
+        if (!isfinite((double)Lv)) sbad += 1.0;
       }
     }
   }
-  double v[5] = {sL, sL2, sA2, sRe, sn};
+  double v[6] = {sL, sL2, sA2, sRe, sn, sbad};
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
+  for (int q = 0; q < 6; ++q) {
     double r = block_sum_256(v[q], red);
     if (threadIdx.x == 0) atomicAdd(a.sums + q, r);
   }
@@ -627,6 +628,7 @@ extern "C" int nkfb_logpsi(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
                            int64_t B, const double local_states[2], void *out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_logpsi");
   int rc = check_net(h, net);
   if (rc) return rc;
   rc = check_op(h, op, net->n_visible);
@@ -659,6 +661,7 @@ extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const
                                    void *rho1, double *sums, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_infidelity_fwd");
   int rc = check_net(h, psi);
   if (rc) return rc;
   rc = check_net(h, phi);
@@ -696,6 +699,7 @@ extern "C" int nkfb_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, cons
                                     const void *rho1, const double *sums, double *grad_acc, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_infidelity_grad");
   int rc = check_net(h, psi);
   if (rc) return rc;
   rc = check_op(h, op2, psi->n_visible);
@@ -729,6 +733,7 @@ extern "C" int nkfb_weighted_score(nkfb_handle_t h, const nkfb_rbm_t *net, const
                                    const double local_states[2], const void *weights, double *acc, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_weighted_score");
   int rc = check_net(h, net);
   if (rc) return rc;
   if (S <= 0) return NKFB_OK;
@@ -768,6 +773,7 @@ extern "C" int nkfb_grad_finalize_centred(nkfb_handle_t h, const double *acc1, c
                                           void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_grad_finalize_centred");
   if (!acc1 || !acc2 || !sums || !centre_sums || !grad_out || P <= 0) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad finalize arguments");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (int)std::min<int64_t>((2 * P + 255) / 256, 1024);
@@ -785,6 +791,7 @@ extern "C" int nkfb_grad_finalize(nkfb_handle_t h, const double *grad_acc, const
                                   void *grad_out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_grad_finalize");
   if (!grad_acc || !sums || !grad_out || P <= 0) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad finalize arguments");
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (int)std::min<int64_t>((2 * P + 255) / 256, 1024);

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   const float ssum = a.s0 + a.s1;
   const int W32 = (g.N + 31) >> 5;
   const int cols = 2 * g.M;
-  double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0;
+  double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0, sbad = 0;  // sbad: local estimators that are NaN or infinite
 
   for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
     // accumulators: [tile][eval] with eval 0 = (psi,sigma) 1 = (psi,eta) 2 = (phi,sigma) 3 = (phi,eta); flips for 1,2,3
@@ -339,13 +339,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
         sA2 += (double)A2;
         sRe += (double)A.re;
         sn += 1.0;
+        if (!isfinite(Lv)) sbad += 1.0;
       }
     }
   }
 
-  double v[5] = {sL, sL2, sA2, sRe, sn};
+  double v[6] = {sL, sL2, sA2, sRe, sn, sbad};
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
+  for (int q = 0; q < 6; ++q) {
     double r = block_sum_256(v[q], red);
     if (threadIdx.x == 0) atomicAdd(a.sums + q, r);
   }

@@ -52,6 +52,7 @@ extern "C" int nkfb_renyi2(nkfb_handle_t h, const nkfb_rbm_t *net, const uint32_
                            void *scratch_logpsi, void *q, double *sums, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_renyi2");
   if (!net || !samples || !mask || !scratch || !scratch_logpsi || !q || !sums)
     NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
   if (S_half <= 0) return NKFB_OK;

@@ -487,6 +487,7 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
                            unsigned long long *n_accepted, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_sample");
   if (!net || !net->kernel || !cfg) NKFB_FAIL(h, NKFB_ERR_INVALID, "null argument");
   if (net->dtype != NKFB_F32 && net->dtype != NKFB_F64) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM dtype");
   if (net->n_visible < 1 || net->n_hidden < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM shape");

@@ -6,6 +6,7 @@
 #include "sampler_ratio.cuh"
 #if NKFB_L == 32
 #include "sampler_lean.cuh"
+#include "sampler_lean_tma.cuh"
 #endif
 
 namespace nkfb {
@@ -72,7 +73,9 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
     } else if (cta_ok && getenv("NKFB_RATIO_NOSPLIT")) {
       head = legacy_big ? a.n_chains : 0;
     } else if (cta_ok && CC == 2 && sizeof(NKFB_RT) == 4) {
-      const double wave = 1.70;  // 6.65 ms per wave; 6.78 ms for 1.73 rounds, 12.9 ms for 3.46 (C4 shards of 8 and 4 GPUs)
+      // one wave of the CTA-synchronous kernel in rounds of the pipelined one (3.92 ms per round at the C4 shape): 1.70 for
+      // the round-1 kernel (6.65 ms per wave), 1.39 for the lean kernel with TMA row staging (5.46 ms)
+      const double wave = getenv("NKFB_NOLEAN") ? 1.70 : 1.39;
       double best = (double)((blocks + slots - 1) / slots) * wave;  // CTA-synchronous kernel alone
       int64_t best_head = a.n_chains;
       for (int64_t k = full_waves; k >= 0; --k) {
@@ -104,7 +107,13 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
       if constexpr (sizeof(NKFB_RT) == 4 && CC == 2) lean = !getenv("NKFB_NOLEAN");
       if constexpr (sizeof(NKFB_RT) == 4 && CC == 2) {
         // single precision, two chains per warp: the lean form of the CTA-synchronous kernel (sampler_lean.cuh)
-        if (lean)
+        // default: rows staged by the TMA unit with an mbarrier pipeline (sampler_lean_tma.cuh, 21.8 ms per launch at
+        // C4); NKFB_LEAN_TMA=0: the cp.async form (sampler_lean.cuh, 22.6 ms)
+        const char *tma = getenv("NKFB_LEAN_TMA");
+        if (lean && !(tma && atoi(tma) == 0))
+          rc = gl_one ? launch_ratio_lean_tma<NP, 2, 1, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st)
+                      : launch_ratio_lean_tma<NP, 2, GW, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st);
+        else if (lean)
           rc = gl_one ? launch_ratio_lean<NP, 2, 1>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st)
                       : launch_ratio_lean<NP, 2, GW>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st);
       }
@@ -188,6 +197,9 @@ int NKFB_FN(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP, i
       case 53: return launch_ratio_lean<7, 2, 4, 4, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
       case 54: return launch_ratio_lean<7, 2, 7, 8, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
       case 55: return launch_ratio_lean<7, 2, 7, 8, 16, 1>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 56: return launch_ratio_lean_tma<7, 2, 4, 8, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 57: return launch_ratio_lean_tma<7, 2, 4, 8, 16, 4>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
+      case 58: return launch_ratio_lean_tma<7, 2, 4, 4, 16, 2>(h, net, a, ws, a.site_seq, (const float *)a.a0_seq, st);
       case 44: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 45: return launch_ratio_cta<NKFB_RT, 7, 1, 2, 32, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);
       case 46: return launch_ratio_cta<NKFB_RT, 7, 1, 4, 24, 1>(h, net, a, ws, a.site_seq, (const NKFB_RT *)a.a0_seq, st);

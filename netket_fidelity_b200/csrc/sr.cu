@@ -103,6 +103,7 @@ extern "C" int nkfb_score_dot(nkfb_handle_t h, const nkfb_rbm_t *net, const uint
                               const double local_states[2], const void *vec, void *out, void *stream) {
   if (!h) return NKFB_ERR_INVALID;
   NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_score_dot");
   if (!net || !net->kernel || net->n_visible < 1 || net->n_hidden < 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM");
   if (net->dtype != NKFB_F32 && net->dtype != NKFB_F64) NKFB_FAIL(h, NKFB_ERR_INVALID, "bad RBM dtype");
   if (S <= 0) return NKFB_OK;

@@ -210,9 +210,10 @@ class InfidelityStep:
         CUDA graph; later `step()` calls replay it: one launch instead of ~18, which is what small problems
         (BASELINE C1 / C2: a step is a few hundred microseconds of kernels) are bound by.  The parameters are read
         from the buffers of `psi` / `phi` at replay time, so in-place optimiser updates are seen; the Metropolis
-        step counter lives on the device (nkfb_sample_cfg_t.step_offset_dev).  Single rank only."""
-        if self.world != 1:
-            raise RuntimeError("capture_graph: single-rank only (the all-reduces are not captured)")
+        step counter lives on the device (nkfb_sample_cfg_t.step_offset_dev)."""
+        # multi-rank: the NCCL all-reduces of the step are captured with it (torch's NCCL process group records them
+        # into the graph; the eager warm-up steps below have already initialised the communicator).  Every rank must
+        # call capture_graph / step collectively.
         if self._graph is not None:
             return
         if not self.initialised:

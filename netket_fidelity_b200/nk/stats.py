@@ -11,12 +11,15 @@ class Stats:
                  R_hat=math.nan, tau_corr_max=math.nan):
         self.mean, self.error_of_mean, self.variance = mean, error_of_mean, variance
         self.tau_corr, self.R_hat, self.tau_corr_max = tau_corr, R_hat, tau_corr_max
+        self.n_nonfinite = 0     # local estimators that were NaN / infinite (counted by the estimator kernel, sums[5])
 
     def replace(self, **kw):
         d = dict(mean=self.mean, error_of_mean=self.error_of_mean, variance=self.variance, tau_corr=self.tau_corr,
                  R_hat=self.R_hat, tau_corr_max=self.tau_corr_max)
         d.update(kw)
-        return Stats(**d)
+        out = Stats(**d)
+        out.n_nonfinite = self.n_nonfinite
+        return out
 
     def to_dict(self):
         return {"Mean": _f(self.mean), "Variance": _f(self.variance), "Sigma": _f(self.error_of_mean),

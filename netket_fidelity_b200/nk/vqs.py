@@ -328,8 +328,21 @@ class MCState(_RBMStateBase):
             n_glob = s[4]
             mean = s[0] / n_glob
             var = max(0.0, s[1] / n_glob - mean * mean)
+            if var < 1e-10 * mean * mean:
+                # converged regime (F -> 1, cv = -1/2): the variance is far below mean^2 and the one-pass form
+                # sum L^2 / n - mean^2 has cancelled; recompute it centred (one more reduction, rarely taken)
+                c2 = ((L.double() - mean) ** 2).sum().reshape(1)
+                if self._world > 1:
+                    from ..parallel import allreduce_sum_
+                    allreduce_sum_(c2)
+                var = float(c2.item()) / n_glob
             st = stats_from_partials(part, rows, cols, l_block, n_blocks, var * rows * cols)
             st.mean, st.variance = float(mean), float(var)
+            st.n_nonfinite = int(s[5])
+            if st.n_nonfinite:
+                import warnings
+                warnings.warn(f"{st.n_nonfinite} local estimators are NaN or infinite (diverged parameters?)",
+                              RuntimeWarning, stacklevel=3)
             return st
         mean = tot / S
         tot2 = float(((L.double() - mean) ** 2).sum().item())

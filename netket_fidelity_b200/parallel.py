@@ -4,7 +4,7 @@ The path shards over Markov chains exactly like the reference's MPI scheme (NetK
 `n_chains_per_rank`; gradient mean at infidelity/overlap/expect.py:126): rank r owns the global
 chains [r * n_local, (r+1) * n_local) of BOTH families.  Two sums cross the interconnect per step:
 
-  1. eight doubles  [sum L, sum L^2, sum |A|^2, sum Re A, n, 0, 0, 0]  after pass A, so that every rank
+  1. eight doubles  [sum L, sum L^2, sum |A|^2, sum Re A, n, n_bad, 0, 0]  after pass A, so that every rank
      centres the score term with the GLOBAL mean F (what NetKet's mpi_statistics does);
   2. the 2P-double gradient accumulator after pass B; then I_grad = -acc / n on every rank.
 

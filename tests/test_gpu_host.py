@@ -318,3 +318,24 @@ def test_examples_run_short():
     I = np.asarray(log.data["Infidelity"]["Mean"] if isinstance(log.data["Infidelity"], dict) else
                    [v for v in log.data["Infidelity"]])
     assert I.ravel()[-1] < 0.5 * I.ravel()[0]
+
+
+def test_nonfinite_local_estimators_are_counted():
+    """sums[5] of nkfb_infidelity_fwd: a NaN parameter makes every local estimator NaN; the kernels count them and the
+    public Stats carries the count (the reference has no such guard; test/_finite_diff.py:18,28 only asserts)."""
+    import warnings
+    hi = nk.hilbert.Spin(0.5, 6)
+    sa = nk.sampler.MetropolisLocal(hi, n_chains=16)
+    ma = nk.models.RBM(alpha=1, param_dtype=complex)
+    psi = nk.vqs.MCState(sa, ma, n_samples=256, seed=1)
+    phi = nk.vqs.MCState(sa, ma, n_samples=256, seed=2)
+    op = nkf.InfidelityOperator(phi, cv_coeff=-0.5)
+    assert psi.expect(op).n_nonfinite == 0
+    psi.samples_packed()                                   # keep these samples, then poison one parameter
+    smp = psi._samples_packed
+    psi._flat[0] = float("nan")
+    psi._samples_packed = smp
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        st = psi.expect(op)
+    assert st.n_nonfinite == 256 and any("NaN" in str(x.message) for x in w)
