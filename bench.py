@@ -217,7 +217,7 @@ class Ctx:
         return float(t.item())
 
 
-def make_engine(ctx, name, dtype, site_mode):
+def make_engine(ctx, name, dtype, site_mode, one_collective=False):
     from netket_fidelity_b200 import _native as nv
     from netket_fidelity_b200.engine import InfidelityStep, StepConfig
     from netket_fidelity_b200.workloads import make_workload, device_ops, random_rbm
@@ -226,7 +226,8 @@ def make_engine(ctx, name, dtype, site_mode):
     N, M = w["N"], w["M"]
     cd = torch.complex64 if dtype == "f32" else torch.complex128
     U, Ud = device_ops(w, ctx.dev)
-    cfg = StepConfig(w["n_chains"], w["chain_length"], 5, N, seed=20261019, cv_coeff=-0.5, site_mode=site_mode)
+    cfg = StepConfig(w["n_chains"], w["chain_length"], 5, N, seed=20261019, cv_coeff=-0.5, site_mode=site_mode,
+                     one_collective=one_collective)
     eng = InfidelityStep(N, M, cfg, w["mode"], U, Ud, device=ctx.dev, cdtype=cd)
     host = {k: random_rbm(N, M, seed, cd, w["vb"]) for k, seed in (("psi", 1234), ("phi", 5678))}
     devp = {k: [t.to(ctx.dev) if t is not None else None for t in v] for k, v in host.items()}
@@ -388,7 +389,7 @@ def run_b200(args):
     infid = 1.0 - s[0] / s[4]
     acc_rate = eng.n_accepted.sum().item() / (2.0 * eng.local_chains * (5 + w["chain_length"]) * N * eng.steps_done)
     graph_ms = None
-    if args.graph:
+    if args.graph and world == 1:
         # the same K steps replayed from ONE captured CUDA graph per step (engine.capture_graph)
         eng.capture_graph(specs["psi"], specs["phi"])
         for _ in range(3):
@@ -465,7 +466,17 @@ def run_b200(args):
     ffma = max(h.microbench(3, 4096), 1.0)
     mufu = max(h.microbench(0, 2048), 1.0)
     dfma = max(h.microbench(6, 2048), 1.0)
-    f64_block, others = None, {}
+    f64_block, others, one_coll = None, {}, None
+    if not args.no_others and world > 1 and w["mode"] == "upsi":
+        # the same step with ONE all-reduce (engine option one_collective): pass B centred with the previous
+        # step's F plus sum_s conj O_k(sigma_s); reported beside the two-collective headline, not instead of it
+        _, eng1, _, _, specs1, _ = make_engine(ctx, args.workload, args.dtype, args.site_mode, one_collective=True)
+        r1 = time_engine(ctx, eng1, specs1, max(3, min(5, args.steps)), 3)
+        one_coll = {"ms_per_step": r1["ms_per_step"], "value": eng1.S_total / (r1["ms_per_step"] * 1e-3), "unit": UNIT,
+                    "collectives_per_step": 1,
+                    "note": "one all-reduce over [sums | acc1 | acc2] (8 + 4P doubles) instead of 8 doubles + 2P doubles; "
+                            "costs the sigma half of pass B once more"}
+        del eng1, specs1
     if not args.no_others:
         if args.dtype == "f32":
             w64, eng64, _, _, specs64, _ = make_engine(ctx, args.workload, "f64", args.site_mode)
@@ -549,6 +560,7 @@ def run_b200(args):
                                "note": "one captured CUDA graph per step, replayed (not the headline `value`)"}}
                if graph_ms else {}),
             **({"f64": f64_block} if f64_block else {}),
+            **({"one_collective": one_coll} if one_coll else {}),
             **({"other_workloads": others} if others else {}),
         }
         if world == 1 and not args.no_cpu_baseline:

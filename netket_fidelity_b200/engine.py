@@ -211,9 +211,10 @@ class InfidelityStep:
         (BASELINE C1 / C2: a step is a few hundred microseconds of kernels) are bound by.  The parameters are read
         from the buffers of `psi` / `phi` at replay time, so in-place optimiser updates are seen; the Metropolis
         step counter lives on the device (nkfb_sample_cfg_t.step_offset_dev)."""
-        # multi-rank: the NCCL all-reduces of the step are captured with it (torch's NCCL process group records them
-        # into the graph; the eager warm-up steps below have already initialised the communicator).  Every rank must
-        # call capture_graph / step collectively.
+        # Single rank only.  Capturing the step of a multi-rank job (with torch's NCCL all-reduces inside the graph) was
+        # tried in round 2 and hung on 2 GPUs (gpurun call 176: no progress for 15 min), so it stays refused.
+        if self.world != 1:
+            raise RuntimeError("capture_graph: single-rank only (capturing the NCCL all-reduces hung on 2 GPUs)")
         if self._graph is not None:
             return
         if not self.initialised:

@@ -1,14 +1,17 @@
 #!/bin/bash
 # Round-end measurements on one B200 (run under gpurun from the repo root):  bash tools/final_measure.sh TAG
-# 1. the bench line (no profiler), 2. the ncu launch list of a short run, 3. ncu --set full of the three kernels of a step
-TAG=${1:-r01}
+# 1. the bench line (no profiler), 2. the ncu launch list of a short run, 3. ncu --set full of the three kernels of a step,
+# 4. compute-sanitizer memcheck of the smallest configuration (C1 through the public API)
+TAG=${1:-r02}
 mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err || exit 1
 cat gpurun_out/bench_${TAG}.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:sample_ratio_cta_kernel -c 1 -f -o gpurun_out/prof_${TAG}_sampler \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}_sampler.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/ncu_launches_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sample_ratio_lean -c 1 -f -o gpurun_out/prof_${TAG}_sampler \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/ncu_full_${TAG}_sampler.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'infid_fwd_tc_kernel|infid_grad_tc_kernel' -c 2 -f -o gpurun_out/prof_${TAG}_tc \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}_tc.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/ncu_full_${TAG}_tc.log 2>&1
 ls -la gpurun_out/prof_${TAG}_*.ncu-rep
+compute-sanitizer --tool memcheck --error-exitcode 1 python tools/sanitize_c1.py > gpurun_out/sanitizer_${TAG}.log 2>&1
+echo "compute-sanitizer rc=$?"; tail -5 gpurun_out/sanitizer_${TAG}.log

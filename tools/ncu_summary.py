@@ -41,3 +41,20 @@ for r in rows[2:]:
                 pass
     st.sort(reverse=True)
     print("\nwarp stalls per issued instruction: " + ", ".join(f"{n} {v:.2f}" for v, n in st[:8]) + "\n")
+
+# optional second argument: also write the DRAM traffic of the FIRST kernel of the report as JSON (what bench.py reads
+# for `roofline.traffic`): python tools/ncu_summary.py rep.ncu-rep profiles/ncu_sampler_traffic.json
+if len(sys.argv) > 2 and len(rows) > 2:
+    import json
+    r = rows[2]
+
+    def val(key):
+        i = hdr.index(key)
+        v, u = float(r[i]), units[i].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+
+    json.dump({"kernel": r[hdr.index("Kernel Name")][:120], "dram_bytes_read": val("dram__bytes_read.sum"),
+               "dram_bytes_write": val("dram__bytes_write.sum"), "duration_ms_under_ncu": float(r[hdr.index("gpu__time_duration.sum")]),
+               "source": f"ncu --set full capture {rep} (one launch of the sampler of bench.py's C4 step), summarised by "
+                         f"tools/ncu_summary.py into profiles/"},
+              open(sys.argv[2], "w"), indent=1)
