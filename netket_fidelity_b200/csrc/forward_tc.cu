@@ -20,12 +20,18 @@
 namespace nkfb {
 
 // ------------------------------------------------------------------ log-cosh accumulation in product form
+// log cosh z = |x| + log((1 + t e^{-2iy}) / 2) (folded to Re z >= 0).  The factors (1 + t e^{-2iy}) / 2 (|.| <= 1, ~1 for
+// small theta) are multiplied into ONE running complex product per evaluation, whose binary exponent is moved into the
+// real sum every 8 units (two integer operations and two multiplies -- no logarithm, no arctangent inside the loop;
+// round 1 took log + atan2 of the product every 8 units: 21 % of the kernel's instructions, profiles/r02_sass_hist_*).
+// value() takes the one logarithm and the one arctangent at the end, so the phase is defined mod 2 pi as before.
 struct LcAcc {
-  float sx, sy, lr, li;  // sum |x|, sum of the folded y, accumulated log of the flushed products
-  __device__ __forceinline__ void reset() { sx = sy = lr = li = 0.f; }
-  // log cosh z = |x| + log((1 + t e^{-2iy}) / 2) (folded): multiply the running product by (1 + t e^{-2iy}) / 2,
-  // which is ~1 for small theta, so that the log taken every 8 units is small and keeps its absolute accuracy
-  __device__ __forceinline__ void add(float x, float y, float &pr, float &pi) {
+  float sx, sy, pr, pi;  // sum |x| + ln 2 * (exponents taken out of the product), sum of the folded y, running product
+  __device__ __forceinline__ void reset() {
+    sx = sy = pi = 0.f;
+    pr = 1.f;
+  }
+  __device__ __forceinline__ void add(float x, float y) {
     // fold theta to Re >= 0: (x, y) -> (|x|, y sgn x), the sign bit of x moved onto y with one logic operation
     y = __uint_as_float(__float_as_uint(y) ^ (__float_as_uint(x) & 0x80000000u));
     x = fabsf(x);
@@ -52,23 +58,26 @@ struct LcAcc {
     sx += x;
     sy += y;
   }
-  __device__ __forceinline__ void flush(float &pr, float &pi) {
-    lr += 0.5f * logf(fmaf(pr, pr, pi * pi));
-    li += atan2f(pi, pr);
-    pr = 1.f;
-    pi = 0.f;
+  // product <- product * 2^-e, sx <- sx + e ln 2, e = binary exponent of max(|pr|, |pi|): the product stays in [1, 2) x
+  // [0, 2) whatever the number of units (a zero product stays zero and ends as log 0 = -inf, like the log before)
+  __device__ __forceinline__ void renorm() {
+    const int eb = __float_as_int(fmaxf(fabsf(pr), fabsf(pi))) & 0x7F800000;
+    const float sc = __int_as_float(0x7F000000 - eb);
+    pr *= sc;
+    pi *= sc;
+    sx = fmaf((float)((eb >> 23) - 127), 0.69314718055994530942f, sx);
   }
-  __device__ __forceinline__ cx<float> value() const { return mk<float>(sx + lr, sy + li); }
+  __device__ __forceinline__ cx<float> value() const {
+    return mk<float>(sx + 0.5f * logf(fmaf(pr, pr, pi * pi)), sy + atan2f(pi, pr));
+  }
 };
 
 // Epilogue of one (chunk, tile, side): this thread's row, columns [c_begin, c_end) of the chunk (multiples of 8).
-// FLIP: also accumulate the configuration with the gate site flipped (theta + d W[idx, :]);  FULL: every column of
-// the range is a real hidden-unit column (no per-unit bound test; false only for the last chunk).
-// Blocks of 8 units (16 columns) with one flush of the running products each, as before (same numerics).
-template <bool FLIP, bool FULL>
-__device__ __forceinline__ void fwd_epilogue(LcAcc &A0, LcAcc &A1, uint32_t trow, int c_begin, int c_end, int col0,
-                                             int cols, const float *wg, float d) {
-  float p0r = 1.f, p0i = 0.f, p1r = 1.f, p1i = 0.f;
+// FLIP: also accumulate the configuration with the gate site flipped (theta + d W[idx, :]).  Columns beyond 2M (last
+// chunk) need no test: W~ and the staged gate row are zero there, so theta = theta' = 0 and the factor is exactly 1.
+template <bool FLIP>
+__device__ __forceinline__ void fwd_epilogue(LcAcc &A0, LcAcc &A1, uint32_t trow, int c_begin, int c_end, const float *wg,
+                                             float d) {
   int c0 = c_begin;
 #pragma unroll 1
   for (; c0 + 16 <= c_end; c0 += 16) {
@@ -76,26 +85,22 @@ __device__ __forceinline__ void fwd_epilogue(LcAcc &A0, LcAcc &A1, uint32_t trow
     tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      if (FULL || col0 + c0 + 2 * u < cols) {
-        A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
-        if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
-      }
+      A0.add(v[2 * u], v[2 * u + 1]);
+      if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]));
     }
-    A0.flush(p0r, p0i);
-    if (FLIP) A1.flush(p1r, p1i);
+    A0.renorm();
+    if (FLIP) A1.renorm();
   }
   if (c0 < c_end) {  // a last block of 8 columns
     float v[8];
     tmem_ld8(trow + (uint32_t)c0, v);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (FULL || col0 + c0 + 2 * u < cols) {
-        A0.add(v[2 * u], v[2 * u + 1], p0r, p0i);
-        if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]), p1r, p1i);
-      }
+      A0.add(v[2 * u], v[2 * u + 1]);
+      if (FLIP) A1.add(fmaf(d, wg[c0 + 2 * u], v[2 * u]), fmaf(d, wg[c0 + 2 * u + 1], v[2 * u + 1]));
     }
-    A0.flush(p0r, p0i);
-    if (FLIP) A1.flush(p1r, p1i);
+    A0.renorm();
+    if (FLIP) A1.renorm();
   }
 }
 
@@ -113,44 +118,68 @@ struct TcFwdArgs {
   const __nv_bfloat16 *prep_psi, *prep_phi;
   TcGeom g;
   int64_t n_groups;
-  int single_load;  // X tile: one packed-row load per thread (tc_build_x_tile)
-  int tmem_cols;    // TMEM columns this CTA allocates
+  int tmem_cols;  // TMEM columns this CTA allocates
 };
 
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+// TMA bulk copy global -> shared (SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tc_bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+// FM: bit e - 1 set <=> evaluation e (1 = (psi, eta) with U2, 2 = (phi, sigma) with U1, 3 = (phi, eta) with U4) goes
+// through a gate, i.e. has a second (flipped) connected element.  A template parameter so that each of the 16
+// unrolled (network, tile, side) phases carries exactly one epilogue body (the kernel was 51 000 SASS instructions
+// with both bodies and the log / atan2 flushes inlined; `no_instruction` stalls 0.65 per issued instruction).
+template <int FM>
 __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGeom g = a.g;
-  unsigned char *Bs = smem;                             // 3 splits of the current chunk
+  unsigned char *Bs = smem;                             // 3 splits of the current chunk (written by TMA bulk copies only)
   unsigned char *As = Bs + g.b_chunk_bytes();           // X tile
-  uint4 *xtab = reinterpret_cast<uint4 *>(As + g.a_bytes());  // 256 x 16 B: bf16 images of 8 spins (tc_build_x_tile)
-  float *wg = reinterpret_cast<float *>(xtab + 256);        // [2][NN] floats: row `idx` of W (this chunk) for the gate flip
+  uint4 *xtab = reinterpret_cast<uint4 *>(As + g.a_bytes());  // 256 x 16 B: bf16 images of 8 spins (tc_build_x_tile_fast)
+  float *wg = reinterpret_cast<float *>(xtab + 256);        // [2][NN] floats: row `idx` of W (this chunk), per side
   cx<float> *xch = reinterpret_cast<cx<float> *>(wg + 2 * g.NN);  // exchange buffer [7][TC_ROWS]
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar, mbar_b;
   __shared__ uint32_t tmem_base_sh;
   __shared__ double red[8];
+  __shared__ __align__(16) uint4 xtail[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;  // TMEM lane == sample row of the tile
   const int half = warp >> 2;              // which half of the chunk's columns this thread reduces
-  const uint32_t mbar_a = smem_u32(&mbar);
+  const uint32_t mbar_a = smem_u32(&mbar), mbar_ba = smem_u32(&mbar_b);
+  const uint32_t b_bytes = (uint32_t)g.b_chunk_bytes();
 
   if (tid == 0) {
     mbar_init(mbar_a, 1);
+    mbar_init(mbar_ba, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int64_t)blockIdx.x < a.n_groups) {  // first chunk of the first network on its way while the tables are filled
+      tc_mbar_expect_tx(mbar_ba, b_bytes);
+      tc_bulk_g2s(smem_u32(Bs), a.prep_psi, b_bytes, mbar_ba);
+    }
   }
   // 256 columns per CTA (two CTAs share the SM's 512); all 512 when the CTA is alone on its SM (a.tmem_cols)
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), a.tmem_cols);
   tc_fill_x_table(xtab, a.s0, a.s1);
+  tc_fill_x_tail(xtail, g.N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
   const uint32_t idesc = umma_idesc_bf16_f32(TC_ROWS, g.NN, 0, 0);
-  uint32_t parity = 0;
+  uint32_t parity = 0, parity_b = 0;
 
   const float ssum = a.s0 + a.s1;
   const int W32 = (g.N + 31) >> 5;
   const int cols = 2 * g.M;
+  const bool dbuf = 2 * g.NN <= a.tmem_cols;
   double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0, sbad = 0;  // sbad: local estimators that are NaN or infinite
 
   for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
@@ -167,42 +196,41 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
 #pragma unroll
     for (int netid = 0; netid < 2; ++netid) {
       const NetDev<float> &net = netid == 0 ? psi : phi;
-      const __nv_bfloat16 *prep = netid == 0 ? a.prep_psi : a.prep_phi;
 #pragma unroll 1
       for (int chunk = 0; chunk < g.NC; ++chunk) {
-        __syncthreads();  // everyone is done with the previous chunk's Bs / wg
-        {                 // stage the three bf16 splits of this chunk
-          const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(prep) +
-                                                             (size_t)chunk * g.b_chunk_bytes());
-          uint4 *dst = reinterpret_cast<uint4 *>(Bs);
-          const int n16 = (int)(g.b_chunk_bytes() / 16);
-          for (int i = tid; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
+        __syncthreads();  // everyone is done with the previous chunk's gate rows
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {  // row `idx` of W for the evaluations of this network that flip a spin
+          const int ev = netid * 2 + side;
+          if (ev != 0 && ((FM >> (ev - 1)) & 1)) {
+            const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+            for (int n = tid; n < g.NN; n += TC_THREADS) {
+              const int col = chunk * g.NN + n;
+              wg[side * g.NN + n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
+            }
+          }
         }
         // The 2 TC_T phases (tile, side) of this chunk, software-pipelined when two accumulators fit the CTA's 256
         // TMEM columns: the X tile and the UMMAs of phase p + 1 are issued BEFORE the epilogue of phase p (the X
         // buffer is free as soon as the UMMAs of phase p have completed), so the tensor pipe works under the
         // epilogue instead of in front of it.
-        const bool dbuf = 2 * g.NN <= a.tmem_cols;
         auto issue = [&](int p) {
           const int t = p >> 1, side = p & 1;
-          const int ev = netid * 2 + side;
-          const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
-          const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
           const uint32_t *packed = side == 0 ? a.sigma : a.eta;
           const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
-          if (flip) {
-            float *wgp = wg + (p & 1) * g.NN;
-            for (int n = tid; n < g.NN; n += TC_THREADS) {
-              const int col = chunk * g.NN + n;
-              wgp[n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
-            }
-          }
-          tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, a.single_load != 0, xtab);
+          if (g.KC <= 16)
+            tc_build_x_tile_fast<TC_THREADS / TC_ROWS>(As, packed, s_base, a.S, g, xtab, xtail);
+          else
+            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, false, xtab);
           fence_async_smem();
           tc_fence_before();
           __syncthreads();
           if (tid == 0) {
             tc_fence_after();
+            if (p == 0) {  // this chunk's W~ (TMA bulk copy requested one chunk ahead)
+              mbar_wait(mbar_ba, parity_b);
+              parity_b ^= 1;
+            }
             const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
             const uint32_t td = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u);
             for (int s = 0; s < 3; ++s)
@@ -221,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
           const int t = p >> 1, side = p & 1;
           const int ev = netid * 2 + side;
           const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
-          const bool flip = (ev != 0) && (op.kind == NKFB_OP_GATE);
+          const bool flip = ev != 0 && ((FM >> (ev == 0 ? 0 : ev - 1)) & 1);
           const uint32_t *packed = side == 0 ? a.sigma : a.eta;
           const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
           if (!dbuf) issue(p);
@@ -229,6 +257,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
           parity ^= 1;
           tc_fence_after();
           if (dbuf && p + 1 < 2 * TC_T) issue(p + 1);
+          if (p == 2 * TC_T - 1 && tid == 0) {
+            // every UMMA of this chunk has completed: its W~ buffer is free, so the next chunk (of this network, of the
+            // other one, or the first of the CTA's next group) is requested now and lands under this phase's epilogue
+            const bool last_chunk = chunk + 1 == g.NC;
+            const bool more = !(last_chunk && netid == 1) || grp + gridDim.x < a.n_groups;
+            if (more) {
+              const __nv_bfloat16 *nprep = last_chunk ? (netid == 0 ? a.prep_phi : a.prep_psi) : (netid == 0 ? a.prep_psi : a.prep_phi);
+              const int nchunk = last_chunk ? 0 : chunk + 1;
+              tc_mbar_expect_tx(mbar_ba, b_bytes);
+              tc_bulk_g2s(smem_u32(Bs), reinterpret_cast<const unsigned char *>(nprep) + (size_t)nchunk * b_bytes, b_bytes, mbar_ba);
+            }
+          }
           // ---- epilogue: this thread's row, its half of the chunk's columns
           float d = 0.f;
           if (flip) {
@@ -239,24 +279,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
             }
           }
           LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
-          const int nh = g.NN / 2;  // columns per half (multiple of 8)
+          // columns per half (multiple of 8); the last chunk stops at the last real column (rounded up to 16)
+          const int nh = min(g.NN, ((cols - chunk * g.NN + 15) >> 4) << 4) / 2;
           const uint32_t trow = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u) + ((uint32_t)(32 * (warp & 3)) << 16);
-          const float *wgp = wg + (p & 1) * g.NN;
-          const int cb = half * nh, ce = (half + 1) * nh, col0 = chunk * g.NN;
-          const bool full = col0 + ce <= cols;
-          if (flip) {
-            if (full)
-              fwd_epilogue<true, true>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
-            else
-              fwd_epilogue<true, false>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
-          } else {
-            if (full)
-              fwd_epilogue<false, true>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
-            else
-              fwd_epilogue<false, false>(A0, A1, trow, cb, ce, col0, cols, wgp, d);
-          }
+          const float *wgp = wg + side * g.NN;
+          if (flip)
+            fwd_epilogue<true>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
+          else
+            fwd_epilogue<false>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
           tc_fence_before();
-          __syncthreads();  // this phase's TMEM buffer and gate row may be overwritten now
+          __syncthreads();  // this phase's TMEM buffer may be overwritten now
         }
       }
     }
@@ -271,9 +303,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
         xch[1 * TC_ROWS + row] = acc0[t][1].value();
         xch[2 * TC_ROWS + row] = acc0[t][2].value();
         xch[3 * TC_ROWS + row] = acc0[t][3].value();
-        xch[4 * TC_ROWS + row] = acc1[t][1].value();
-        xch[5 * TC_ROWS + row] = acc1[t][2].value();
-        xch[6 * TC_ROWS + row] = acc1[t][3].value();
+        if (FM & 1) xch[4 * TC_ROWS + row] = acc1[t][1].value();
+        if (FM & 2) xch[5 * TC_ROWS + row] = acc1[t][2].value();
+        if (FM & 4) xch[6 * TC_ROWS + row] = acc1[t][3].value();
       }
       __syncthreads();
       const int64_t gs = s_base + row;
@@ -283,21 +315,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
         for (int e = 0; e < 4; ++e) b0[e] = acc0[t][e].value() + xch[e * TC_ROWS + row];
         b1[0] = mk<float>(0, 0);
 #pragma unroll
-        for (int e = 1; e < 4; ++e) b1[e] = acc1[t][e].value() + xch[(3 + e) * TC_ROWS + row];
+        for (int e = 1; e < 4; ++e)
+          b1[e] = ((FM >> (e - 1)) & 1) ? acc1[t][e].value() + xch[(3 + e) * TC_ROWS + row] : mk<float>(0, 0);
         // visible-bias terms a.x for (psi, sigma) (psi, eta) (phi, sigma) (phi, eta)
         cx<float> ax[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)};
-        for (int i = 0; i < g.N; ++i) {
-          const float xs = ((a.sigma[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
-          const float xe = ((a.eta[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
-          if (psi.a) {
-            const cx<float> ai = mk<float>(psi.a[2 * i], psi.a[2 * i + 1]);
-            ax[0] = ax[0] + xs * ai;
-            ax[1] = ax[1] + xe * ai;
-          }
-          if (phi.a) {
-            const cx<float> ai = mk<float>(phi.a[2 * i], phi.a[2 * i + 1]);
-            ax[2] = ax[2] + xs * ai;
-            ax[3] = ax[3] + xe * ai;
+        if (psi.a || phi.a) {
+          for (int i = 0; i < g.N; ++i) {
+            const float xs = ((a.sigma[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+            const float xe = ((a.eta[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+            if (psi.a) {
+              const cx<float> ai = mk<float>(psi.a[2 * i], psi.a[2 * i + 1]);
+              ax[0] = ax[0] + xs * ai;
+              ax[1] = ax[1] + xe * ai;
+            }
+            if (phi.a) {
+              const cx<float> ai = mk<float>(phi.a[2 * i], phi.a[2 * i + 1]);
+              ax[2] = ax[2] + xs * ai;
+              ax[3] = ax[3] + xe * ai;
+            }
           }
         }
         cx<float> T[4], rho = mk<float>(0, 0);
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
           const NetDev<float> &net = e < 2 ? psi : phi;
           const uint32_t *packed = (e & 1) ? a.eta : a.sigma;
           const cx<float> l0 = b0[e] + ax[e];
-          if (e == 0 || op.kind != NKFB_OP_GATE) {
+          if (e == 0 || !((FM >> (e == 0 ? 0 : e - 1)) & 1)) {
             T[e] = l0;
           } else {
             const int bit = (packed[gs * W32 + (op.idx >> 5)] >> (op.idx & 31)) & 1u;
@@ -418,12 +453,21 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   a.g = g;
   const int64_t tiles = (S + TC_ROWS - 1) / TC_ROWS;
   a.n_groups = (tiles + TC_T - 1) / TC_T;
-  a.single_load = getenv("NKFB_TC_FWD_SINGLE") ? 1 : 0;
   a.tmem_cols = smem > (size_t)115 * 1024 ? 512 : 256;  // more than half of the SM's shared memory: one CTA per SM
-  NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = smem <= 112 * 1024 ? 2 : 1;
   const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);
-  infid_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);
+  // which evaluations go through a gate: bit 0 (psi, eta) U2, bit 1 (phi, sigma) U1, bit 2 (phi, eta) U4
+  const int fm = (a.op2.kind == NKFB_OP_GATE ? 1 : 0) | (a.op1.kind == NKFB_OP_GATE ? 2 : 0) | (a.op4.kind == NKFB_OP_GATE ? 4 : 0);
+#define NKFB_FWD_TC_CASE(FM)                                                                                              \
+  case FM:                                                                                                                \
+    NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel<FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    infid_fwd_tc_kernel<FM><<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);         \
+    break;
+  switch (fm) {
+    NKFB_FWD_TC_CASE(0) NKFB_FWD_TC_CASE(1) NKFB_FWD_TC_CASE(2) NKFB_FWD_TC_CASE(3)
+    NKFB_FWD_TC_CASE(4) NKFB_FWD_TC_CASE(5) NKFB_FWD_TC_CASE(6) NKFB_FWD_TC_CASE(7)
+  }
+#undef NKFB_FWD_TC_CASE
   NKFB_LAUNCHED(h);
   return NKFB_OK;
 }

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
   cx<float> *wts = reinterpret_cast<cx<float> *>(corr + NN);     // [3][128]: w_sig, w_eta, conj(rho1)
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) uint4 xtail[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
     uint4 *az = reinterpret_cast<uint4 *>(As);
     for (int i = tid; i < GX_CHUNKS * TC_ROWS; i += NT) az[i] = make_uint4(0, 0, 0, 0);
     tc_fill_x_table(xtab, a.s0, a.s1);
+    tc_fill_x_tail(xtail, N);
   }
   tc_fence_before();
   __syncthreads();
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1) infid_grad_tc_kernel(NetDev<float> psi,
     for (int side = 0; side < n_sides; ++side) {
       const uint32_t *packed = side == 0 ? a.sigma : a.eta;
       const bool flip = gate && side == 1;
-      tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, true, xtab);
+      tc_build_x_tile_fast<NT / TC_ROWS>(As, packed, s_base, a.S, g, xtab, xtail);  // N + 1 <= 128: KC <= 16
       fence_async_smem();
       tc_fence_before();
       __syncthreads();

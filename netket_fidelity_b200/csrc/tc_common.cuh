@@ -247,6 +247,62 @@ __device__ __forceinline__ void tc_build_x_tile(unsigned char *As, const uint32_
 }
 
 
+// Lean form of the builder for N <= 128 (W32 <= 4, KC <= 16) and NQ * 128 threads: thread t serves row t % 128 and the
+// 8-spin groups kc = t / 128 + NQ m.  One 16-byte (or W32 4-byte) load of the packed row, then per group a byte
+// extraction whose word index and shift are compile-time constants plus 8 (t / 128), one LDS.128 from the spin-group
+// table and one STS.128.  The group that holds the bias row (kc == N / 8: the last N % 8 spins, 1.0 at k = N, zeros
+// behind) is patched with two 16-byte masks (xtail[0] = AND mask, xtail[1] = OR pattern, tc_fill_x_tail); groups beyond
+// it are zero.  Every condition is uniform over a warp.  (The generic loop above spent ~420 instructions per thread
+// and tile on index arithmetic: a quarter of the estimator's instructions, ncu source view, profiles/r02_*.)
+__device__ __forceinline__ void tc_fill_x_tail(uint4 *xtail, int N) {
+  if (threadIdx.x < 8) {
+    const int e = threadIdx.x, r = N & 7;  // element e of the bias group: spins for e < r, 1.0 at e == r, zero behind
+    uint16_t *am = reinterpret_cast<uint16_t *>(xtail), *om = am + 8;
+    am[e] = e < r ? 0xFFFFu : 0u;
+    om[e] = e == r ? 0x3F80u : 0u;
+  }
+}
+
+template <int NQ>
+__device__ __forceinline__ void tc_build_x_tile_fast(unsigned char *As, const uint32_t *packed, int64_t s_base, int64_t S,
+                                                     const TcGeom &g, const uint4 *xtab, const uint4 *xtail) {
+  const int r = threadIdx.x & (TC_ROWS - 1), q = threadIdx.x / TC_ROWS;
+  const int W32 = (g.N + 31) >> 5, kt = g.N >> 3;
+  const int64_t gs = s_base + r;
+  uint4 *dst = reinterpret_cast<uint4 *>(As) + r;
+  if (gs >= S) {  // rows beyond the batch (last tile only): zero
+#pragma unroll
+    for (int m = 0; m < 16 / NQ; ++m)
+      if (q + NQ * m < g.KC) dst[(q + NQ * m) * TC_ROWS] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  uint32_t wd[4] = {0u, 0u, 0u, 0u};
+  if (W32 == 4 && (reinterpret_cast<uintptr_t>(packed) & 15u) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(packed + gs * 4));
+    wd[0] = v.x, wd[1] = v.y, wd[2] = v.z, wd[3] = v.w;
+  } else {
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      if (w < W32) wd[w] = __ldg(packed + gs * W32 + w);
+  }
+  const uint4 tand = xtail[0], tor = xtail[1];
+#pragma unroll
+  for (int m = 0; m < 16 / NQ; ++m) {
+    const int kc = q + NQ * m;
+    if (kc < g.KC) {
+      const uint32_t bits = (wd[(NQ * m) >> 2] >> ((((NQ * m) & 3) + q) * 8)) & 0xFFu;
+      uint4 e = xtab[bits];
+      if (kc >= kt) {
+        if (kc == kt)
+          e = make_uint4((e.x & tand.x) | tor.x, (e.y & tand.y) | tor.y, (e.z & tand.z) | tor.z, (e.w & tand.w) | tor.w);
+        else
+          e = make_uint4(0, 0, 0, 0);
+      }
+      dst[kc * TC_ROWS] = e;
+    }
+  }
+}
+
 inline bool bf16_exact(double v) {
   const float f = (float)v;
   uint32_t u;
