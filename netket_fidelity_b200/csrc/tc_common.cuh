@@ -25,7 +25,7 @@ struct TcGeom {
 // cols: real columns to cover; extra_col_bytes: additional shared memory per column (pass B keeps the three
 // bf16 splits of a 128-sample Y tile); x_bytes: bytes of the X tile
 inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_bytes = 0, size_t x_bytes = 0,
-                        size_t budget_bytes = 200 * 1024, int nn_quantum = 16) {
+                        size_t budget_bytes = 200 * 1024, int nn_quantum = 16, int nn_cap = 256) {
   g->N = N;
   g->M = M;
   g->KT = ((N + 1 + 15) / 16) * 16;
@@ -35,7 +35,7 @@ inline bool tc_geometry(int N, int M, TcGeom *g, int cols, size_t extra_col_byte
   // columns per chunk: multiple of 16, <= 256, and everything must fit in shared memory
   if (budget_bytes < x_bytes + 8192 + 4096) return false;
   const size_t budget = budget_bytes - x_bytes - 8192;
-  int nn_max = (int)std::min<size_t>(256, budget / ((size_t)3 * g->KC * 16 + extra_col_bytes));
+  int nn_max = (int)std::min<size_t>((size_t)nn_cap, budget / ((size_t)3 * g->KC * 16 + extra_col_bytes));
   nn_max = (nn_max / nn_quantum) * nn_quantum;
   if (nn_max < nn_quantum) return false;
   g->NC = (cols + nn_max - 1) / nn_max;
