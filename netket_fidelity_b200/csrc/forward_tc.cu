@@ -136,34 +136,45 @@ __device__ __forceinline__ void tc_bulk_g2s(uint32_t dst_smem, const void *src, 
 // through a gate, i.e. has a second (flipped) connected element.  A template parameter so that each of the 16
 // unrolled (network, tile, side) phases carries exactly one epilogue body (the kernel was 51 000 SASS instructions
 // with both bodies and the log / atan2 flushes inlined; `no_instruction` stalls 0.65 per issued instruction).
+//
+// Roles (round 2): warps 0..7 build the X tiles and run the log-cosh epilogues; warp 8 issues the TMA bulk copies of
+// the W~ chunks and the UMMAs.  Phases q = 0, 1, 2, ... run over (group, network, chunk, tile, side); the hand-offs are
+// mbarriers, there is no CTA barrier in the loop:
+//   mbar_x  (8 arrivals, one per epilogue warp)  X tile of phase q written (and, before a chunk's first phase, its gate
+//           rows); its completion also tells the issuer that every warp is past epilogue q - 2: TMEM buffer q & 1 is free
+//   mbar_b  (bytes)   W~ chunk landed                       mbar_a  (tcgen05.commit)  UMMAs of phase q complete
+// An epilogue warp in phase q: wait a(q) -> X tile q + 1 -> arrive x -> epilogue q, so the tensor pipe computes phase
+// q + 1 under the epilogue of phase q (two accumulators in TMEM).  With thread 0 of warp 0 issuing the UMMAs (21 per
+// phase plus their descriptors) that warp reached every CTA barrier late: `barrier` was the top stall (1.6 per issued
+// instruction, ncu profiles/r02_*).
+constexpr int TC_FWD_THREADS = TC_THREADS + 32;
+
 template <int FM>
-__global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
+__global__ void __launch_bounds__(TC_FWD_THREADS, 2) infid_fwd_tc_kernel(NetDev<float> psi, NetDev<float> phi, TcFwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGeom g = a.g;
   unsigned char *Bs = smem;                             // 3 splits of the current chunk (written by TMA bulk copies only)
   unsigned char *As = Bs + g.b_chunk_bytes();           // X tile
   uint4 *xtab = reinterpret_cast<uint4 *>(As + g.a_bytes());  // 256 x 16 B: bf16 images of 8 spins (tc_build_x_tile_fast)
-  float *wg = reinterpret_cast<float *>(xtab + 256);        // [2][NN] floats: row `idx` of W (this chunk), per side
-  cx<float> *xch = reinterpret_cast<cx<float> *>(wg + 2 * g.NN);  // exchange buffer [7][TC_ROWS]
-  __shared__ __align__(8) uint64_t mbar, mbar_b;
+  float *wg = reinterpret_cast<float *>(xtab + 256);        // [2 chunk parities][2 sides][NN] floats: row `idx` of W
+  cx<float> *xch = reinterpret_cast<cx<float> *>(wg + 4 * g.NN);  // exchange buffer [7][TC_ROWS]
+  __shared__ __align__(8) uint64_t mbar, mbar_b, mbar_x;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ double red[8];
+  __shared__ double red[16];
   __shared__ __align__(16) uint4 xtail[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;  // TMEM lane == sample row of the tile
-  const int half = warp >> 2;              // which half of the chunk's columns this thread reduces
-  const uint32_t mbar_a = smem_u32(&mbar), mbar_ba = smem_u32(&mbar_b);
+  const int half = (warp >> 2) & 1;        // which half of the chunk's columns this thread reduces
+  const bool issuer = warp == TC_THREADS / 32;
+  const uint32_t mbar_a = smem_u32(&mbar), mbar_ba = smem_u32(&mbar_b), mbar_xa = smem_u32(&mbar_x);
   const uint32_t b_bytes = (uint32_t)g.b_chunk_bytes();
 
   if (tid == 0) {
     mbar_init(mbar_a, 1);
     mbar_init(mbar_ba, 1);
+    mbar_init(mbar_xa, TC_THREADS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((int64_t)blockIdx.x < a.n_groups) {  // first chunk of the first network on its way while the tables are filled
-      tc_mbar_expect_tx(mbar_ba, b_bytes);
-      tc_bulk_g2s(smem_u32(Bs), a.prep_psi, b_bytes, mbar_ba);
-    }
   }
   // 256 columns per CTA (two CTAs share the SM's 512); all 512 when the CTA is alone on its SM (a.tmem_cols)
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_sh), a.tmem_cols);
@@ -174,7 +185,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
   const uint32_t idesc = umma_idesc_bf16_f32(TC_ROWS, g.NN, 0, 0);
-  uint32_t parity = 0, parity_b = 0;
 
   const float ssum = a.s0 + a.s1;
   const int W32 = (g.N + 31) >> 5;
@@ -182,199 +192,237 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   const bool dbuf = 2 * g.NN <= a.tmem_cols;
   double sL = 0, sL2 = 0, sA2 = 0, sRe = 0, sn = 0, sbad = 0;  // sbad: local estimators that are NaN or infinite
 
-  for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
-    // accumulators: [tile][eval] with eval 0 = (psi,sigma) 1 = (psi,eta) 2 = (phi,sigma) 3 = (phi,eta); flips for 1,2,3
-    LcAcc acc0[TC_T][4], acc1[TC_T][4];
-#pragma unroll
-    for (int t = 0; t < TC_T; ++t)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc0[t][e].reset();
-        acc1[t][e].reset();
-      }
-
-#pragma unroll
-    for (int netid = 0; netid < 2; ++netid) {
-      const NetDev<float> &net = netid == 0 ? psi : phi;
-#pragma unroll 1
-      for (int chunk = 0; chunk < g.NC; ++chunk) {
-        __syncthreads();  // everyone is done with the previous chunk's gate rows
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {  // row `idx` of W for the evaluations of this network that flip a spin
-          const int ev = netid * 2 + side;
-          if (ev != 0 && ((FM >> (ev - 1)) & 1)) {
-            const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
-            for (int n = tid; n < g.NN; n += TC_THREADS) {
-              const int col = chunk * g.NN + n;
-              wg[side * g.NN + n] = col < cols ? net.W[(int64_t)op.idx * cols + col] : 0.f;
-            }
-          }
-        }
-        // The 2 TC_T phases (tile, side) of this chunk, software-pipelined when two accumulators fit the CTA's 256
-        // TMEM columns: the X tile and the UMMAs of phase p + 1 are issued BEFORE the epilogue of phase p (the X
-        // buffer is free as soon as the UMMAs of phase p have completed), so the tensor pipe works under the
-        // epilogue instead of in front of it.
-        auto issue = [&](int p) {
-          const int t = p >> 1, side = p & 1;
-          const uint32_t *packed = side == 0 ? a.sigma : a.eta;
-          const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
-          if (g.KC <= 16)
-            tc_build_x_tile_fast<TC_THREADS / TC_ROWS>(As, packed, s_base, a.S, g, xtab, xtail);
-          else
-            tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, false, xtab);
-          fence_async_smem();
-          tc_fence_before();
-          __syncthreads();
-          if (tid == 0) {
+  if (issuer) {
+    // ------------------------------------------------------------------------------------------ the issuing warp
+    uint32_t q = 0, cc = 0;  // phase counter, chunk counter
+    if (lane == 0 && (int64_t)blockIdx.x < a.n_groups) {
+      tc_mbar_expect_tx(mbar_ba, b_bytes);
+      tc_bulk_g2s(smem_u32(Bs), a.prep_psi, b_bytes, mbar_ba);
+    }
+    for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      for (int netid = 0; netid < 2; ++netid) {
+        for (int chunk = 0; chunk < g.NC; ++chunk, ++cc) {
+          for (int p = 0; p < 2 * TC_T; ++p, ++q) {
+            mbar_wait(mbar_xa, q & 1);  // X tile of phase q written; every warp is past epilogue q - 2
+            if (p == 0) mbar_wait(mbar_ba, cc & 1);  // this chunk's W~
             tc_fence_after();
-            if (p == 0) {  // this chunk's W~ (TMA bulk copy requested one chunk ahead)
-              mbar_wait(mbar_ba, parity_b);
-              parity_b ^= 1;
+            if (lane == 0) {
+              const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+              const uint32_t td = tmem_d + (dbuf ? (uint32_t)((q & 1) * g.NN) : 0u);
+              for (int s = 0; s < 3; ++s)
+                for (int ks = 0; ks < g.KS; ++ks) {
+                  const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                  const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (g.NN * 16),
+                                                g.NN * 16, 128);
+                  umma_bf16(td, ad, bd, idesc, (s | ks) ? 1u : 0u);
+                }
+              umma_commit(mbar_a);
             }
-            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
-            const uint32_t td = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u);
-            for (int s = 0; s < 3; ++s)
-              for (int ks = 0; ks < g.KS; ++ks) {
-                const uint64_t ad = umma_desc(a_base + ks * 2 * (TC_ROWS * 16), TC_ROWS * 16, 128);
-                const uint64_t bd = umma_desc(b_base + s * (uint32_t)g.b_split_bytes() + ks * 2 * (g.NN * 16),
-                                              g.NN * 16, 128);
-                umma_bf16(td, ad, bd, idesc, (s | ks) ? 1u : 0u);
+            __syncwarp();
+            if (p == 2 * TC_T - 1) {
+              // every UMMA of this chunk must complete before its W~ buffer is overwritten by the next chunk (of this
+              // network, of the other one, or the first of the CTA's next group): requested now, lands under the epilogue
+              mbar_wait(mbar_a, q & 1);
+              const bool last_chunk = chunk + 1 == g.NC;
+              const bool more = !(last_chunk && netid == 1) || grp + gridDim.x < a.n_groups;
+              if (more && lane == 0) {
+                const __nv_bfloat16 *nprep = (last_chunk ? 1 - netid : netid) == 0 ? a.prep_psi : a.prep_phi;
+                const int nchunk = last_chunk ? 0 : chunk + 1;
+                tc_mbar_expect_tx(mbar_ba, b_bytes);
+                tc_bulk_g2s(smem_u32(Bs), reinterpret_cast<const unsigned char *>(nprep) + (size_t)nchunk * b_bytes, b_bytes,
+                            mbar_ba);
               }
-            umma_commit(mbar_a);
-          }
-        };
-        if (dbuf) issue(0);
-#pragma unroll
-        for (int p = 0; p < 2 * TC_T; ++p) {
-          const int t = p >> 1, side = p & 1;
-          const int ev = netid * 2 + side;
-          const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
-          const bool flip = ev != 0 && ((FM >> (ev == 0 ? 0 : ev - 1)) & 1);
-          const uint32_t *packed = side == 0 ? a.sigma : a.eta;
-          const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
-          if (!dbuf) issue(p);
-          mbar_wait(mbar_a, parity);
-          parity ^= 1;
-          tc_fence_after();
-          if (dbuf && p + 1 < 2 * TC_T) issue(p + 1);
-          if (p == 2 * TC_T - 1 && tid == 0) {
-            // every UMMA of this chunk has completed: its W~ buffer is free, so the next chunk (of this network, of the
-            // other one, or the first of the CTA's next group) is requested now and lands under this phase's epilogue
-            const bool last_chunk = chunk + 1 == g.NC;
-            const bool more = !(last_chunk && netid == 1) || grp + gridDim.x < a.n_groups;
-            if (more) {
-              const __nv_bfloat16 *nprep = last_chunk ? (netid == 0 ? a.prep_phi : a.prep_psi) : (netid == 0 ? a.prep_psi : a.prep_phi);
-              const int nchunk = last_chunk ? 0 : chunk + 1;
-              tc_mbar_expect_tx(mbar_ba, b_bytes);
-              tc_bulk_g2s(smem_u32(Bs), reinterpret_cast<const unsigned char *>(nprep) + (size_t)nchunk * b_bytes, b_bytes, mbar_ba);
             }
           }
-          // ---- epilogue: this thread's row, its half of the chunk's columns
-          float d = 0.f;
-          if (flip) {
-            const int64_t gs = s_base + row;
-            if (gs < a.S) {
-              const uint32_t w = packed[gs * W32 + (op.idx >> 5)];
-              d = ssum - 2.f * (((w >> (op.idx & 31)) & 1u) ? a.s1 : a.s0);
-            }
-          }
-          LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
-          // columns per half (multiple of 8); the last chunk stops at the last real column (rounded up to 16)
-          const int nh = min(g.NN, ((cols - chunk * g.NN + 15) >> 4) << 4) / 2;
-          const uint32_t trow = tmem_d + (dbuf ? (uint32_t)((p & 1) * g.NN) : 0u) + ((uint32_t)(32 * (warp & 3)) << 16);
-          const float *wgp = wg + side * g.NN;
-          if (flip)
-            fwd_epilogue<true>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
-          else
-            fwd_epilogue<false>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
-          tc_fence_before();
-          __syncthreads();  // this phase's TMEM buffer may be overwritten now
         }
       }
     }
-
-    // ---- combine the two column halves, add the visible-bias terms, finish the estimator
+  } else {
+    // ------------------------------------------------------------------------------------------ the epilogue warps
+    uint32_t q = 0, cc = 0;
+    // this warp's writes to shared memory are done and visible to the tensor pipe: one arrive per warp
+    auto warp_arrive_x = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(mbar_xa) : "memory");
+    };
+    // row `idx` of W (columns of chunk `chunk_n` of network `netid_n`) for the evaluations that flip a spin
+    auto stage_wg = [&](int netid_n, int chunk_n, uint32_t cc_n) {
 #pragma unroll
-    for (int t = 0; t < TC_T; ++t) {
-      const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
-      __syncthreads();
-      if (half == 1) {
-        xch[0 * TC_ROWS + row] = acc0[t][0].value();
-        xch[1 * TC_ROWS + row] = acc0[t][1].value();
-        xch[2 * TC_ROWS + row] = acc0[t][2].value();
-        xch[3 * TC_ROWS + row] = acc0[t][3].value();
-        if (FM & 1) xch[4 * TC_ROWS + row] = acc1[t][1].value();
-        if (FM & 2) xch[5 * TC_ROWS + row] = acc1[t][2].value();
-        if (FM & 4) xch[6 * TC_ROWS + row] = acc1[t][3].value();
-      }
-      __syncthreads();
-      const int64_t gs = s_base + row;
-      if (half == 0 && gs < a.S) {
-        cx<float> b0[4], b1[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) b0[e] = acc0[t][e].value() + xch[e * TC_ROWS + row];
-        b1[0] = mk<float>(0, 0);
-#pragma unroll
-        for (int e = 1; e < 4; ++e)
-          b1[e] = ((FM >> (e - 1)) & 1) ? acc1[t][e].value() + xch[(3 + e) * TC_ROWS + row] : mk<float>(0, 0);
-        // visible-bias terms a.x for (psi, sigma) (psi, eta) (phi, sigma) (phi, eta)
-        cx<float> ax[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)};
-        if (psi.a || phi.a) {
-          for (int i = 0; i < g.N; ++i) {
-            const float xs = ((a.sigma[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
-            const float xe = ((a.eta[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
-            if (psi.a) {
-              const cx<float> ai = mk<float>(psi.a[2 * i], psi.a[2 * i + 1]);
-              ax[0] = ax[0] + xs * ai;
-              ax[1] = ax[1] + xe * ai;
-            }
-            if (phi.a) {
-              const cx<float> ai = mk<float>(phi.a[2 * i], phi.a[2 * i + 1]);
-              ax[2] = ax[2] + xs * ai;
-              ax[3] = ax[3] + xe * ai;
-            }
+      for (int side = 0; side < 2; ++side) {
+        const int ev = netid_n * 2 + side;
+        if (ev != 0 && ((FM >> (ev - 1)) & 1)) {
+          const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+          const float *Wn = netid_n == 0 ? psi.W : phi.W;
+          float *dst = wg + ((cc_n & 1) * 2 + side) * g.NN;
+          for (int n = tid; n < g.NN; n += TC_THREADS) {
+            const int col = chunk_n * g.NN + n;
+            dst[n] = col < cols ? Wn[(int64_t)op.idx * cols + col] : 0.f;
           }
         }
-        cx<float> T[4], rho = mk<float>(0, 0);
+      }
+    };
+    auto build_x = [&](int64_t grp_n, int p_n) {
+      const int t = p_n >> 1, side = p_n & 1;
+      const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+      const int64_t s_base = (grp_n * TC_T + t) * TC_ROWS;
+      if (g.KC <= 16)
+        tc_build_x_tile_fast<TC_THREADS / TC_ROWS>(As, packed, s_base, a.S, g, xtab, xtail);
+      else
+        tc_build_x_tile(As, packed, s_base, a.S, g, a.s0, a.s1, false, xtab);
+    };
+    if ((int64_t)blockIdx.x < a.n_groups) {  // prologue: gate rows of the first chunk, X tile of phase 0
+      stage_wg(0, 0, 0);
+      build_x(blockIdx.x, 0);
+      warp_arrive_x();
+    }
+
+    for (int64_t grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      // accumulators: [tile][eval] with eval 0 = (psi,sigma) 1 = (psi,eta) 2 = (phi,sigma) 3 = (phi,eta); flips for 1,2,3
+      LcAcc acc0[TC_T][4], acc1[TC_T][4];
+#pragma unroll
+      for (int t = 0; t < TC_T; ++t)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const OpDev &op = (e == 1) ? a.op2 : (e == 2 ? a.op1 : a.op4);
-          const NetDev<float> &net = e < 2 ? psi : phi;
-          const uint32_t *packed = (e & 1) ? a.eta : a.sigma;
-          const cx<float> l0 = b0[e] + ax[e];
-          if (e == 0 || !((FM >> (e == 0 ? 0 : e - 1)) & 1)) {
-            T[e] = l0;
-          } else {
-            const int bit = (packed[gs * W32 + (op.idx >> 5)] >> (op.idx & 31)) & 1u;
-            const float dd = ssum - 2.f * (bit ? a.s1 : a.s0);
-            cx<float> l1 = b1[e] + ax[e];
-            if (net.a) l1 = l1 + dd * mk<float>(net.a[2 * op.idx], net.a[2 * op.idx + 1]);
-            const cx<float> m0 = mk<float>((float)op.gate_mel[bit][0][0], (float)op.gate_mel[bit][0][1]);
-            const cx<float> m1 = mk<float>((float)op.gate_mel[bit][1][0], (float)op.gate_mel[bit][1][1]);
-            const float amax = fmaxf(l0.re, l1.re);
-            const cx<float> e0 = m0 * cexp(mk<float>(l0.re - amax, l0.im));
-            const cx<float> e1 = m1 * cexp(mk<float>(l1.re - amax, l1.im));
-            const cx<float> sum = e0 + e1;
-            T[e] = clog(sum);
-            T[e].re += amax;
-            if (e == 1) rho = (1.f / abs2(sum)) * (e1 * conj(sum));
+          acc0[t][e].reset();
+          acc1[t][e].reset();
+        }
+
+#pragma unroll
+      for (int netid = 0; netid < 2; ++netid) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < g.NC; ++chunk, ++cc) {
+          // columns per half (multiple of 8); the last chunk stops at the last real column (rounded up to 16)
+          const int nh = min(g.NN, ((cols - chunk * g.NN + 15) >> 4) << 4) / 2;
+#pragma unroll
+          for (int p = 0; p < 2 * TC_T; ++p, ++q) {
+            const int t = p >> 1, side = p & 1;
+            const int ev = netid * 2 + side;
+            const OpDev &op = (ev == 1) ? a.op2 : (ev == 2 ? a.op1 : a.op4);
+            const bool flip = ev != 0 && ((FM >> (ev == 0 ? 0 : ev - 1)) & 1);
+            const uint32_t *packed = side == 0 ? a.sigma : a.eta;
+            const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+            // what phase q + 1 is: next (tile, side) of this chunk, the first of the next chunk / network, or of the next group
+            const bool last_chunk = chunk + 1 == g.NC;
+            const bool more = p + 1 < 2 * TC_T || !(last_chunk && netid == 1) || grp + gridDim.x < a.n_groups;
+            auto next_phase = [&]() {
+              if (!more) return;
+              if (p + 1 < 2 * TC_T) {
+                build_x(grp, p + 1);
+              } else {
+                stage_wg(last_chunk ? 1 - netid : netid, last_chunk ? 0 : chunk + 1, cc + 1);
+                build_x((last_chunk && netid == 1) ? grp + gridDim.x : grp, 0);
+              }
+              warp_arrive_x();
+            };
+            mbar_wait(mbar_a, q & 1);  // UMMAs of phase q complete: the X buffer is free, the accumulator is ready
+            tc_fence_after();
+            if (dbuf) next_phase();
+            // ---- epilogue: this thread's row, its half of the chunk's columns
+            float d = 0.f;
+            if (flip) {
+              const int64_t gs = s_base + row;
+              if (gs < a.S) {
+                const uint32_t w = packed[gs * W32 + (op.idx >> 5)];
+                d = ssum - 2.f * (((w >> (op.idx & 31)) & 1u) ? a.s1 : a.s0);
+              }
+            }
+            LcAcc &A0 = acc0[t][ev], &A1 = acc1[t][ev];
+            const uint32_t trow = tmem_d + (dbuf ? (uint32_t)((q & 1) * g.NN) : 0u) + ((uint32_t)(32 * (warp & 3)) << 16);
+            const float *wgp = wg + ((cc & 1) * 2 + side) * g.NN;
+            if (flip)
+              fwd_epilogue<true>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
+            else
+              fwd_epilogue<false>(A0, A1, trow, half * nh, (half + 1) * nh, wgp, d);
+            if (!dbuf) next_phase();  // one accumulator: the next UMMAs may only start after this epilogue
           }
         }
-        // l = T(phi,sigma) + T(psi,eta) - T(psi,sigma) - T(phi,eta)
-        const cx<float> l = T[2] + T[1] - T[0] - T[3];
-        const cx<float> A = cexp(l);
-        const float A2 = abs2(A);
-        float Lv = A.re;
-        if (a.has_cv) Lv += a.cv * (A2 - 1.f);
-        a.log_val[gs] = l;
-        a.L[gs] = Lv;
-        a.rho1[gs] = rho;
-        sL += (double)Lv;
-        sL2 += (double)Lv * (double)Lv;
-        sA2 += (double)A2;
-        sRe += (double)A.re;
-        sn += 1.0;
-        if (!isfinite(Lv)) sbad += 1.0;
+      }
+
+      // ---- combine the two column halves, add the visible-bias terms, finish the estimator
+#pragma unroll
+      for (int t = 0; t < TC_T; ++t) {
+        const int64_t s_base = (grp * TC_T + t) * TC_ROWS;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");  // the epilogue warps only
+        if (half == 1) {
+          xch[0 * TC_ROWS + row] = acc0[t][0].value();
+          xch[1 * TC_ROWS + row] = acc0[t][1].value();
+          xch[2 * TC_ROWS + row] = acc0[t][2].value();
+          xch[3 * TC_ROWS + row] = acc0[t][3].value();
+          if (FM & 1) xch[4 * TC_ROWS + row] = acc1[t][1].value();
+          if (FM & 2) xch[5 * TC_ROWS + row] = acc1[t][2].value();
+          if (FM & 4) xch[6 * TC_ROWS + row] = acc1[t][3].value();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");
+        const int64_t gs = s_base + row;
+        if (half == 0 && gs < a.S) {
+          cx<float> b0[4], b1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) b0[e] = acc0[t][e].value() + xch[e * TC_ROWS + row];
+          b1[0] = mk<float>(0, 0);
+#pragma unroll
+          for (int e = 1; e < 4; ++e)
+            b1[e] = ((FM >> (e - 1)) & 1) ? acc1[t][e].value() + xch[(3 + e) * TC_ROWS + row] : mk<float>(0, 0);
+          // visible-bias terms a.x for (psi, sigma) (psi, eta) (phi, sigma) (phi, eta)
+          cx<float> ax[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)};
+          if (psi.a || phi.a) {
+            for (int i = 0; i < g.N; ++i) {
+              const float xs = ((a.sigma[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+              const float xe = ((a.eta[gs * W32 + (i >> 5)] >> (i & 31)) & 1u) ? a.s1 : a.s0;
+              if (psi.a) {
+                const cx<float> ai = mk<float>(psi.a[2 * i], psi.a[2 * i + 1]);
+                ax[0] = ax[0] + xs * ai;
+                ax[1] = ax[1] + xe * ai;
+              }
+              if (phi.a) {
+                const cx<float> ai = mk<float>(phi.a[2 * i], phi.a[2 * i + 1]);
+                ax[2] = ax[2] + xs * ai;
+                ax[3] = ax[3] + xe * ai;
+              }
+            }
+          }
+          cx<float> T[4], rho = mk<float>(0, 0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const OpDev &op = (e == 1) ? a.op2 : (e == 2 ? a.op1 : a.op4);
+            const NetDev<float> &net = e < 2 ? psi : phi;
+            const uint32_t *packed = (e & 1) ? a.eta : a.sigma;
+            const cx<float> l0 = b0[e] + ax[e];
+            if (e == 0 || !((FM >> (e == 0 ? 0 : e - 1)) & 1)) {
+              T[e] = l0;
+            } else {
+              const int bit = (packed[gs * W32 + (op.idx >> 5)] >> (op.idx & 31)) & 1u;
+              const float dd = ssum - 2.f * (bit ? a.s1 : a.s0);
+              cx<float> l1 = b1[e] + ax[e];
+              if (net.a) l1 = l1 + dd * mk<float>(net.a[2 * op.idx], net.a[2 * op.idx + 1]);
+              const cx<float> m0 = mk<float>((float)op.gate_mel[bit][0][0], (float)op.gate_mel[bit][0][1]);
+              const cx<float> m1 = mk<float>((float)op.gate_mel[bit][1][0], (float)op.gate_mel[bit][1][1]);
+              const float amax = fmaxf(l0.re, l1.re);
+              const cx<float> e0 = m0 * cexp(mk<float>(l0.re - amax, l0.im));
+              const cx<float> e1 = m1 * cexp(mk<float>(l1.re - amax, l1.im));
+              const cx<float> sum = e0 + e1;
+              T[e] = clog(sum);
+              T[e].re += amax;
+              if (e == 1) rho = (1.f / abs2(sum)) * (e1 * conj(sum));
+            }
+          }
+          // l = T(phi,sigma) + T(psi,eta) - T(psi,sigma) - T(phi,eta)
+          const cx<float> l = T[2] + T[1] - T[0] - T[3];
+          const cx<float> A = cexp(l);
+          const float A2 = abs2(A);
+          float Lv = A.re;
+          if (a.has_cv) Lv += a.cv * (A2 - 1.f);
+          a.log_val[gs] = l;
+          a.L[gs] = Lv;
+          a.rho1[gs] = rho;
+          sL += (double)Lv;
+          sL2 += (double)Lv * (double)Lv;
+          sA2 += (double)A2;
+          sRe += (double)A.re;
+          sn += 1.0;
+          if (!isfinite(Lv)) sbad += 1.0;
+        }
       }
     }
   }
@@ -382,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) infid_fwd_tc_kernel(NetDev<floa
   double v[6] = {sL, sL2, sA2, sRe, sn, sbad};
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
-    double r = block_sum_256(v[q], red);
+    double r = block_sum_256(v[q], red);  // all 9 warps (the issuing warp adds zeros)
     if (threadIdx.x == 0) atomicAdd(a.sums + q, r);
   }
   tc_fence_before();
@@ -411,7 +459,7 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb, budget) &&
       !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb))
     return 1;
-  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 8 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
+  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 16 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
   if (smem > 227 * 1024) return 1;
 
   // prepared bf16 splits of both networks live in the handle's second workspace
@@ -461,7 +509,7 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
 #define NKFB_FWD_TC_CASE(FM)                                                                                              \
   case FM:                                                                                                                \
     NKFB_CHECK_CUDA(h, cudaFuncSetAttribute(infid_fwd_tc_kernel<FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    infid_fwd_tc_kernel<FM><<<grid, TC_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);         \
+    infid_fwd_tc_kernel<FM><<<grid, TC_FWD_THREADS, smem, st>>>(make_netdev<float>(psi), make_netdev<float>(phi), a);         \
     break;
   switch (fm) {
     NKFB_FWD_TC_CASE(0) NKFB_FWD_TC_CASE(1) NKFB_FWD_TC_CASE(2) NKFB_FWD_TC_CASE(3)
