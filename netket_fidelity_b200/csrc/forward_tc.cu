@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 2) infid_fwd_tc_kernel(NetDev<
         for (int chunk = 0; chunk < g.NC; ++chunk, ++cc) {
           for (int p = 0; p < 2 * TC_T; ++p, ++q) {
             mbar_wait(mbar_xa, q & 1);  // X tile of phase q written; every warp is past epilogue q - 2
-            if (p == 0) mbar_wait(mbar_ba, cc & 1);  // this chunk's W~
+            if (p == 0) mbar_wait_relaxed(mbar_ba, cc & 1);  // this chunk's W~
             tc_fence_after();
             if (lane == 0) {
               const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 2) infid_fwd_tc_kernel(NetDev<
             if (p == 2 * TC_T - 1) {
               // every UMMA of this chunk must complete before its W~ buffer is overwritten by the next chunk (of this
               // network, of the other one, or the first of the CTA's next group): requested now, lands under the epilogue
-              mbar_wait(mbar_a, q & 1);
+              mbar_wait_relaxed(mbar_a, q & 1);
               const bool last_chunk = chunk + 1 == g.NC;
               const bool more = !(last_chunk && netid == 1) || grp + gridDim.x < a.n_groups;
               if (more && lane == 0) {

@@ -92,6 +92,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// the same wait for a warp that has nothing else to do (the UMMA-issuing warp): sleep between polls so that its spin
+// does not take issue slots from the epilogue warps of its sub-partition (a tight try_wait loop ran at 0.22 IPC)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra RDONE;\n\t"
+      "RWAIT_LOOP:\n\t"
+      "nanosleep.u32 128;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra RDONE;\n\t"
+      "bra RWAIT_LOOP;\n\t"
+      "RDONE:\n\t"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
