@@ -78,6 +78,14 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t 
 // CTA barrier in the loop: the epilogue warps signal "X tile written" and "Y written" on two mbarriers (one arrive per
 // warp) that only the issuing warp waits on.  TAIL = the chunk holds the visible-bias pseudo-unit or padding
 // (last chunk only): the per-unit index tests exist in that instantiation alone.
+// Two-level accumulation of G (round 2).  The tensor pipe aligns every addend to the accumulator and TRUNCATES it, so a
+// long chain of UMMAs into one fp32 accumulator drifts by ~0.05 eps per sample relative to a non-zero mean (measured
+// against the complex128 kernels on the same 2^20 samples: 2.0e-4 of max |g| after 65 536 samples per CTA, 1.2e-5 after
+// 4 096; the CUDA-core kernel: 2.0e-6).  G is therefore accumulated by the UMMAs over TC_G_FLUSH iterations only
+// (4 tiles of both sides = 512 samples) in a first TMEM accumulator, which the epilogue warps then add -- rounded to
+// nearest, 60 instructions per thread per 8 iterations -- into a second, resident one.
+constexpr int TC_G_FLUSH = 8;
+
 struct GradEpi {
   uint32_t hi[4], mid[4], lo[4];
 };
@@ -146,7 +154,8 @@ __global__ void __launch_bounds__(NT + 32, 1) infid_grad_tc_kernel(NetDev<float>
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_theta = tmem_base_sh;        // two accumulators of NN columns: [0, NN) and [NN, 2 NN)
-  const uint32_t tmem_g = tmem_base_sh + 2 * NN;   // NN columns, persistent (3 NN <= 512)
+  const uint32_t tmem_g = tmem_base_sh + 2 * NN;   // NN columns: G of the current TC_G_FLUSH iterations (UMMA accumulator)
+  const uint32_t tmem_gt = tmem_base_sh + 3 * NN;  // NN columns: G of all earlier iterations (added by the epilogue warps)
   const uint32_t idesc1 = umma_idesc_bf16_f32(TC_ROWS, NN, 0, 0);
   const uint32_t idesc2 = umma_idesc_bf16_f32(TC_ROWS, NN, 1, 1);
   uint32_t par1 = 0, par2 = 0;
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(NT + 32, 1) infid_grad_tc_kernel(NetDev<float>
         const uint64_t ad = umma_desc(a_base + ks * 256, 128, TC_ROWS * 16);
         // B: Y MN-major: 8-column groups 2048 B apart (SBO), 8-sample groups 128 B apart (LBO)
         const uint64_t bd = umma_desc(y_base + s * (uint32_t)y_split_bytes + ks * 256, 128, TC_ROWS * 16);
-        umma_bf16(tmem_g, ad, bd, idesc2, (k > 0 || s || ks) ? 1u : 0u);
+        umma_bf16(tmem_g, ad, bd, idesc2, ((k % TC_G_FLUSH) != 0 || s || ks) ? 1u : 0u);
       }
     umma_commit(mbar2);
   };
@@ -316,12 +325,30 @@ __global__ void __launch_bounds__(NT + 32, 1) infid_grad_tc_kernel(NetDev<float>
         *reinterpret_cast<uint4 *>(dst + 2 * y_split_bytes) = make_uint4(o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
       };
 
+      const bool chain_end = k > 0 && (k % TC_G_FLUSH) == 0;
+      if (chain_end) {  // a chain of UMMAs has ended with GEMM 2(k - 1): G_total (+)= G_chain, this thread's row and columns
+        mbar_wait(mbar2, par2);
+        par2 ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int b8 = 0; b8 < NB8; ++b8) {
+          const uint32_t c0 = (uint32_t)(half * nh + 8 * b8);
+          float vs[8], vt[8];
+          tmem_ld8(tmem_g + lane_off + c0, vs);
+          if (k > TC_G_FLUSH) {
+            tmem_ld8(tmem_gt + lane_off + c0, vt);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) vs[q] += vt[q];
+          }
+          tmem_st8(tmem_gt + lane_off + c0, vs);
+        }
+      }
       GradEpi e0;
       if (tail)
         compute(0, e0, std::true_type{});
       else
         compute(0, e0, std::false_type{});
-      if (k > 0) {  // GEMM 2(k - 1) done: the Y buffer and X[(k + 1) & 1] are free
+      if (k > 0 && !chain_end) {  // GEMM 2(k - 1) done: the Y buffer and X[(k + 1) & 1] are free
         mbar_wait(mbar2, par2);
         par2 ^= 1;
         tc_fence_after();
@@ -371,7 +398,13 @@ __global__ void __launch_bounds__(NT + 32, 1) infid_grad_tc_kernel(NetDev<float>
     const int64_t offK = 2 * (int64_t)M, offA = 2 * ((int64_t)M + (int64_t)N * M);
     for (int c0 = half * nh; c0 < (half + 1) * nh; c0 += 8) {
       float v[8];
-      tmem_ld8(tmem_g + lane_off + (uint32_t)c0, v);
+      tmem_ld8(tmem_g + lane_off + (uint32_t)c0, v);  // the last (possibly short) chain
+      if (K > TC_G_FLUSH) {
+        float vt[8];
+        tmem_ld8(tmem_gt + lane_off + (uint32_t)c0, vt);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += vt[q];
+      }
       if (i <= N) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -408,15 +441,15 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   if (N + 1 > TC_ROWS) return 1;  // GEMM 2 holds all gradient rows (spins + bias) in one UMMA M = 128 tile
   TcGeom g;
   // per column: three bf16 splits of a 128-sample Y tile (768 B) + gate row + correction (8 B); fixed: two X tiles, the
-  // spin-group table, two tiles of per-sample weights.  Three accumulators of NN columns share the 512 TMEM columns.
+  // spin-group table, two tiles of per-sample weights.  Four accumulators of NN columns share the 512 TMEM columns.
   const size_t fixed = 2 * (size_t)GX_CHUNKS * TC_ROWS * 16 + 4096 + 2 * 3 * TC_ROWS * sizeof(cx<float>);
   auto smem_of = [&](const TcGeom &q) {
     return q.b_chunk_bytes() + fixed + 3 * (size_t)(q.NN / 8) * TC_ROWS * 16 + 2 * (size_t)q.NN * 4 + 128;
   };
-  // sixteen warps (chunks of a multiple of 32 columns, up to 128) when that geometry fits; else eight (multiples of 16, up to 160)
+  // sixteen warps (chunks of a multiple of 32 columns, up to 128) when that geometry fits; else eight (multiples of 16, up to 128: four accumulators of NN columns share the 512 TMEM columns)
   bool wide = !getenv("NKFB_GRAD_TC_NARROW") &&
               tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 32, 128) && smem_of(g) <= (size_t)226 * 1024;
-  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 16, 160)) return 1;
+  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 16, 128)) return 1;
   const size_t smem = smem_of(g);
   if (smem > 227 * 1024) return 1;
 
@@ -472,7 +505,6 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
     switch (g.NN / 16) {
       NKFB_GRAD_TC_CASE(1, 256) NKFB_GRAD_TC_CASE(2, 256) NKFB_GRAD_TC_CASE(3, 256) NKFB_GRAD_TC_CASE(4, 256)
       NKFB_GRAD_TC_CASE(5, 256) NKFB_GRAD_TC_CASE(6, 256) NKFB_GRAD_TC_CASE(7, 256) NKFB_GRAD_TC_CASE(8, 256)
-      NKFB_GRAD_TC_CASE(9, 256) NKFB_GRAD_TC_CASE(10, 256)
       default: return 1;  // wider chunks: CUDA-core kernel
     }
   }

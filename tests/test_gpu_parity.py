@@ -180,14 +180,16 @@ def test_infidelity_fwd_and_grad_fixed_batch(h, N, M, S, cd, cv):
         ref = infidelity_and_grad(psi, phi, sigma, eta, cv, U1, U2, U4)
         a, b = to_rbmspec(psi, cd), to_rbmspec(phi, cd)
         lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, cv, to_opspec(U1), to_opspec(U2), to_opspec(U4))
-        assert rel_err(L.cpu().numpy(), ref["L"]) <= tol * 10, (mode, U)
+        # north_star's tolerance (1e-10 / 1e-5) on F and on the max-norm gradient; the per-sample estimator, relative to
+        # max |L| over the batch, gets twice that (profiles/r02_parity_errors.txt: worst measured 8.1e-6 in complex64)
+        assert rel_err(L.cpu().numpy(), ref["L"]) <= tol * 2, (mode, U, rel_err(L.cpu().numpy(), ref["L"]))
         s = sums.cpu().numpy()
         assert s[4] == S
         assert abs(s[0] / S - ref["F"]) <= tol * max(1.0, abs(ref["F"]))
         gacc = h.infidelity_grad(a, sp, ep, LS, cv, lv, rho1, sums, to_opspec(U2))
         g = h.grad_finalize(gacc, sums, a.n_params, cd).cpu().numpy()
         gref = ref["grad"].ravel()
-        assert rel_err(g, gref) <= tol * 20, (mode, U, rel_err(g, gref))
+        assert rel_err(g, gref) <= tol * (4 if isinstance(U, oops.IsingLike) else 1), (mode, U, rel_err(g, gref))
 
 
 @pytest.mark.parametrize("cd", [torch.complex128, torch.complex64])
@@ -207,7 +209,7 @@ def test_ising_type_U_dagger_gradient_in_several_chunks(h, cd, monkeypatch):
     monkeypatch.setenv("NKFB_ISING_GRAD_CHUNK", "37")
     gacc = h.infidelity_grad(a, sp, ep, LS, -0.5, lv, rho1, sums, to_opspec(U2))
     g = h.grad_finalize(gacc, sums, a.n_params, cd).cpu().numpy()
-    assert rel_err(g, ref["grad"].ravel()) <= TOL[cd] * 20
+    assert rel_err(g, ref["grad"].ravel()) <= TOL[cd] * 4
 
 
 def test_gradient_without_visible_bias(h):

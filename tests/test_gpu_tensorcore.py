@@ -51,13 +51,16 @@ def test_tc_estimator_and_gradient(h, N, M, S, std, cv):
             s = sums.cpu().numpy()
             out[impl] = (L.cpu().numpy(), s, g, rho1.cpu().numpy())
             assert s[4] == S
-            assert rel_err(out[impl][0], ref["L"]) <= 1e-4, (impl, mode, U)
+            # north_star's complex64 tolerance (1e-5) on F and the max-norm gradient, twice that on the per-sample
+            # estimator relative to max |L| (profiles/r02_parity_errors.txt: tcgen05 worst 5.3e-6 / 4.3e-6, CUDA cores
+            # 8.1e-6 / 1.8e-6 on these batches)
+            assert rel_err(out[impl][0], ref["L"]) <= 2e-5, (impl, mode, U, rel_err(out[impl][0], ref["L"]))
             assert abs(s[0] / S - ref["F"]) <= 1e-5 * max(1.0, abs(ref["F"])), (impl, mode, U)
-            assert rel_err(g, ref["grad"].ravel()) <= 2e-4, (impl, mode, U, rel_err(g, ref["grad"].ravel()))
+            assert rel_err(g, ref["grad"].ravel()) <= 1e-5, (impl, mode, U, rel_err(g, ref["grad"].ravel()))
         os.environ.pop("NKFB_FWD_IMPL")
         os.environ.pop("NKFB_GRAD_IMPL")
         # the two implementations must also agree with each other on the per-sample estimator
-        assert rel_err(out["tc"][0], out["simt"][0]) <= 1e-4
+        assert rel_err(out["tc"][0], out["simt"][0]) <= 2e-5
 
 
 @pytest.mark.parametrize("N,M,S,std", [(100, 400, 4096, 0.01), (20, 200, 2100, 0.05), (37, 90, 2500, 0.05)])
@@ -83,5 +86,5 @@ def test_tc_gradient_eight_and_sixteen_warp_forms_agree(h, monkeypatch, N, M, S,
             monkeypatch.setenv("NKFB_GRAD_TC_NARROW", "1")
         gacc = h.infidelity_grad(a, sp, ep, LS, -0.5, lv, rho1, sums, to_opspec(U2))
         g[form] = h.grad_finalize(gacc, sums, a.n_params, torch.complex64).cpu().numpy()
-        assert rel_err(g[form], ref["grad"].ravel()) <= 2e-4, (form, rel_err(g[form], ref["grad"].ravel()))
+        assert rel_err(g[form], ref["grad"].ravel()) <= 1e-5, (form, rel_err(g[form], ref["grad"].ravel()))
     assert rel_err(g["wide"], g["narrow"]) <= 1e-6, rel_err(g["wide"], g["narrow"])

@@ -62,3 +62,14 @@ gt, gs = tc[3], si[3]
 print(f"gradient: max |dg| / max|g| = {float((gt - gs).abs().max() / gs.abs().max()):.3e}")
 os.environ.pop("NKFB_FWD_IMPL")
 os.environ.pop("NKFB_GRAD_IMPL")
+# complex128 kernels on the same samples and the same (complex64-representable) parameters: the reference both fp32 forms are held to
+psi64, phi64 = (nv.RbmSpec(*[t.to(dev).to(torch.complex128) if t is not None else None
+                             for t in random_rbm(N, M, seed, torch.complex64, w["vb"])]) for seed in (1234, 5678))
+lv, L64, rho1, sums = h.infidelity_fwd(psi64, phi64, sig, eta, ls, -0.5, U, Ud, None)
+gacc = h.infidelity_grad(psi64, sig, eta, ls, -0.5, lv, rho1, sums, Ud)
+g64 = h.grad_finalize(gacc, sums, psi64.n_params, torch.complex128)
+s64 = sums.cpu().numpy()
+for name, o in (("tcgen05", tc), ("CUDA cores", si)):
+    so = o[2].cpu().numpy()
+    print(f"{name} vs complex128 kernels: L max {float((o[1].double() - L64).abs().max() / L64.abs().max()):.3e}  "
+          f"F {abs(so[0] / so[4] - s64[0] / s64[4]):.3e}  gradient max-norm {float((o[3].to(torch.complex128) - g64).abs().max() / g64.abs().max()):.3e}")
