@@ -254,7 +254,10 @@ int dispatch_ratio_f64_L32(nkfb_handle_t, const nkfb_rbm_t *, const SampArgs &, 
 static size_t plain_ws_offset_reals(int N, int M) { return (ratio_ws_reals_max(N, M) + 63) & ~(size_t)63; }
 static size_t seq_ws_offset_reals(int N, int M) { return (plain_ws_offset_reals(N, M) + sampler_ws_reals(N, M) + 63) & ~(size_t)63; }
 // site table of the CTA-synchronous kernel: SITE_SEQ_CAP ints + SITE_SEQ_CAP reals
-static size_t sampler_ws_total_reals(int N, int M) { return seq_ws_offset_reals(N, M) + 2 * (size_t)SITE_SEQ_CAP; }
+// ... followed by the q tables of the half-warp kernel in the 16-lane layout (sampler_lean_hw.cuh)
+static size_t hw_ws_offset_reals(int N, int M) { return (seq_ws_offset_reals(N, M) + 2 * (size_t)SITE_SEQ_CAP + 63) & ~(size_t)63; }
+static size_t sampler_ws_total_reals(int N, int M) { return hw_ws_offset_reals(N, M) + ratio_ws_reals_max(N, M); }
+bool ratio_hw_supported(int NP16);
 
 // lane-group width of the multiplicative sampler: least padded work among the instantiated shapes (<= 8 pairs per
 // lane, <= 16 on 32 lanes in single precision); 0 if the shape is not covered
@@ -316,6 +319,19 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
     NKFB_LAUNCHED(h);
     a.site_seq = site_seq;
     a.a0_seq = a0_seq;
+    // single precision, two chains per warp (6 <= NP <= 8): the half-warp kernel takes the full CTAs of the launch; it
+    // reads its own copy of the q tables in the 16-lane layout (the 32-lane copy serves the chains of the tail)
+    const int NP16 = ratio_pairs(M, 16);
+    if (f32 && NP >= 6 && ratio_hw_supported(NP16) && !getenv("NKFB_NOHW")) {
+      float *ws16 = (float *)ws + hw_ws_offset_reals(N, M);
+      const int64_t tot = (int64_t)2 * N * NP16 * 16;   // tables only: A_i and the range bound come from the 32-lane copy
+      const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+      prep_ratio_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), ws16, 16, NP16, (float)a.s0, (float)a.s1,
+                                                     (size_t)0, (size_t)0, /*tables_only=*/1);
+      NKFB_LAUNCHED(h);
+      a.ws_hw = ws16;
+      a.np_hw = NP16;
+    }
   }
   const int GW = NP < 4 ? NP : 4;
   const float x1 = ratio_xmax(GW), x2 = ratio_xmax(1);

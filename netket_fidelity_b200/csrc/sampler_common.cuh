@@ -26,6 +26,9 @@ struct SampArgs {
   // site_mode 0: proposal sites / A_site of the steps of this call (prep_site_seq), or null
   const int *site_seq;
   const void *a0_seq;
+  // q tables in the 16-lane layout for the half-warp kernel (sampler_lean_hw.cuh), np_hw pairs per lane; or null
+  const void *ws_hw;
+  int np_hw;
   OpDev op;
 };
 

@@ -1,0 +1,52 @@
+// Instantiations of the half-warp lean sampler (sampler_lean_hw.cuh): single precision, shared site sequence, a chain
+// on 16 lanes with NP16 pairs of hidden units per lane (M <= 32 NP16).  Own translation unit: the kernels are fully
+// unrolled and compile in parallel with the 32-lane forms.
+#include <cstdlib>
+
+#include "sampler_lean_hw.cuh"
+
+namespace nkfb {
+
+bool ratio_hw_supported(int NP16) { return NP16 >= 11 && NP16 <= 16; }
+
+template <int NP>
+static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_one, cudaStream_t st) {
+#ifdef NKFB_TUNE
+  if (const char *v = getenv("NKFB_HW_VARIANT")) {
+    if (!gl_one) switch (atoi(v)) {
+      case 1: return launch_ratio_lean_hw<NP, 4, 8, 16, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 2: return launch_ratio_lean_hw<NP, 4, 2, 16, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 3: return launch_ratio_lean_hw<NP, 4, 4, 16, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 4: return launch_ratio_lean_hw<NP, 4, 4, 16, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 5: return launch_ratio_lean_hw<NP, 4, 1, 16, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 6: return launch_ratio_lean_hw<NP, 4, 4, 20, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 7: return launch_ratio_lean_hw<NP, 4, 4, 20, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 8: return launch_ratio_lean_hw<NP, 4, 4, 24, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 9: return launch_ratio_lean_hw<NP, 4, 4, 24, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 10: return launch_ratio_lean_hw<NP, 4, 2, 20, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      case 11: return launch_ratio_lean_hw<NP, 4, 2, 24, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+      default: break;
+    }
+  }
+#endif
+  if (gl_one) return launch_ratio_lean_hw<NP, 1, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  return launch_ratio_lean_hw<NP, 4, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+}
+
+// gl_one = 0: one logarithm per 4 pairs;  gl_one = 1: one logarithm per pair (wider range of X)
+int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, cudaStream_t st) {
+  switch (NP16) {
+#ifndef NKFB_HW_ONLY13
+    case 11: return go_hw<11>(h, net, a, gl_one, st);
+    case 12: return go_hw<12>(h, net, a, gl_one, st);
+    case 14: return go_hw<14>(h, net, a, gl_one, st);
+    case 15: return go_hw<15>(h, net, a, gl_one, st);
+    case 16: return go_hw<16>(h, net, a, gl_one, st);
+#endif
+    case 13: return go_hw<13>(h, net, a, gl_one, st);
+    default: break;
+  }
+  NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "half-warp sampler: %d unit pairs per lane is not instantiated", NP16);
+}
+
+}  // namespace nkfb

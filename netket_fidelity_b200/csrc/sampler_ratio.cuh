@@ -74,12 +74,13 @@ inline float ratio_xmax(int GL) {
 }
 
 template <typename R>
-__global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s1, size_t a0_off, size_t bound_off) {
+__global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s1, size_t a0_off, size_t bound_off,
+                                  int tables_only = 0) {
   const int N = net.N, M = net.M;
   const int64_t slots_per_tab = (int64_t)N * NP * L;
   const int64_t n_slots = 2 * slots_per_tab;
   const double dx = (double)s1 - (double)s0;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_slots + N + M;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_slots + (tables_only ? 0 : N + M);
        idx += (int64_t)gridDim.x * blockDim.x) {
     if (idx < n_slots) {
       const int tab = idx >= slots_per_tab;

@@ -11,6 +11,9 @@
 
 namespace nkfb {
 
+// half-warp lean kernel (sampler_hw_inst.cu): a.ws_hw = q tables in the 16-lane layout, a.np_hw pairs per lane
+int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, cudaStream_t st);
+
 #define NKFB_CAT_(a, b, c) a##b##_L##c
 #define NKFB_CAT(a, b, c) NKFB_CAT_(a, b, c)
 #define NKFB_FN NKFB_CAT(dispatch_ratio_, NKFB_RN, NKFB_L)
@@ -75,7 +78,8 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
     } else if (cta_ok && CC == 2 && sizeof(NKFB_RT) == 4) {
       // one wave of the CTA-synchronous kernel in rounds of the pipelined one (3.92 ms per round at the C4 shape): 1.70 for
       // the round-1 kernel (6.65 ms per wave), 1.39 for the lean kernel with TMA row staging (5.46 ms)
-      const double wave = getenv("NKFB_NOLEAN") ? 1.70 : 1.39;
+      // 1.32 for the half-warp lean kernel (5.16 ms)
+      const double wave = getenv("NKFB_NOLEAN") ? 1.70 : (a.ws_hw != nullptr ? 1.32 : 1.39);
       double best = (double)((blocks + slots - 1) / slots) * wave;  // CTA-synchronous kernel alone
       int64_t best_head = a.n_chains;
       for (int64_t k = full_waves; k >= 0; --k) {
@@ -110,7 +114,9 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
         // default: rows staged by the TMA unit with an mbarrier pipeline (sampler_lean_tma.cuh, 21.8 ms per launch at
         // C4); NKFB_LEAN_TMA=0: the cp.async form (sampler_lean.cuh, 22.6 ms)
         const char *tma = getenv("NKFB_LEAN_TMA");
-        if (lean && !(tma && atoi(tma) == 0))
+        if (lean && a.ws_hw != nullptr)
+          rc = dispatch_ratio_hw_f32(h, net, ah, a.np_hw, gl_one, st);
+        else if (lean && !(tma && atoi(tma) == 0))
           rc = gl_one ? launch_ratio_lean_tma<NP, 2, 1, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st)
                       : launch_ratio_lean_tma<NP, 2, GW, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st);
         else if (lean)

@@ -367,3 +367,65 @@ def test_long_calls_fall_back_from_the_site_table(h, algo):
     b, sb, nb = _run(h, p, torch.complex128, 3, n_sweeps, 0, N, 11)
     np.testing.assert_array_equal(a, b)
     assert na == nb
+
+
+@pytest.fixture
+def hw_kernel(monkeypatch):
+    """Half-warp lean kernel (sampler_lean_hw.cuh) on / off; small launches are forced onto the CTA-synchronous path."""
+    def set_(on):
+        for v in ("NKFB_RATIO_NOCTA", "NKFB_RATIO_NOPIPE", "NKFB_RATIO_NOSPLIT", "NKFB_NOHW"):
+            monkeypatch.delenv(v, raising=False)
+        monkeypatch.setenv("NKFB_RATIO_FORCECTA", "1")
+        if not on:
+            monkeypatch.setenv("NKFB_NOHW", "1")
+    return set_
+
+
+@pytest.mark.parametrize("N,M,B", [(100, 400, 0.0), (100, 400, 5.0), (64, 330, 0.0), (37, 384, 0.0), (100, 448, 0.0),
+                                   (128, 470, 0.0), (40, 512, 0.0), (40, 512, 5.0)])
+def test_half_warp_kernel_agrees_with_the_32_lane_lean_kernel(h, algo, hw_kernel, N, M, B):
+    """sampler_lean_hw.cuh (a chain on 16 lanes, both chains of a warp in one instruction stream) against the 32-lane
+    lean kernel on every instantiated width (11..16 pairs per lane), both range windows (B = 5: one logarithm per
+    pair), a chain count that leaves a half-empty warp and a partial CTA, a non-zero step offset (partial first chunk,
+    RNG batch phase) and chain offset, chains continued over a second call: same Philox streams and decisions up to
+    single-precision rounding of the log-ratio, so nearly all chains emit identical samples and the acceptance agrees;
+    the launch counter proves that the half-warp kernel's table preparation ran."""
+    algo(2)
+    p = _net(N, M, 300 + M, 0.01)
+    if B:
+        p = RBMParams(p.kernel, p.bias + B * np.where(np.arange(M) % 2 == 0, 1.0, -1.0), p.visible_bias)
+    n_chains = 333
+    out = {}
+    for on in (False, True):
+        hw_kernel(on)
+        l0 = h.launches
+        a, st, na = _run(h, p, torch.complex64, n_chains, 3, 1, N, 77, chain_offset=5, step_offset=N + 3)
+        out[on, "launches"] = h.launches - l0
+        b, st, nb = _run(h, p, torch.complex64, n_chains, 2, 0, N, 77, chain_offset=5, step_offset=5 * N + 3, state=st)
+        out[on] = (np.concatenate([a, b], axis=1), st.cpu().numpy(), na + nb)
+    assert out[True, "launches"] == out[False, "launches"] + 1      # the 16-lane copy of the q tables
+    same = np.all(out[True][0].reshape(n_chains, -1) == out[False][0].reshape(n_chains, -1), axis=1).mean()
+    assert same > 0.9, same
+    assert abs(out[True][2] - out[False][2]) < 0.005 * out[False][2]
+    # final configurations are the last samples of the second call
+    np.testing.assert_array_equal(out[True][1].view(np.uint32), out[True][0][:, -1])
+
+
+@pytest.mark.parametrize("M", [400, 512])
+def test_half_warp_kernel_matches_exact_distribution(h, algo, hw_kernel, M):
+    """N = 10 spins with the north-star number of hidden units: the half-warp kernel samples |psi|^2 exactly (z-scores
+    against full enumeration, as test_sampler_matches_exact_distribution)."""
+    algo(2)
+    hw_kernel(True)
+    N = 10
+    p = _net(N, M, 7 * N, 0.5 / np.sqrt(M))
+    n_chains, cl = 4096, 64
+    l0 = h.launches
+    got, _, nacc = _run(h, p, torch.complex64, n_chains, cl, 30, N, 2031)
+    x = unpack_np(got.reshape(-1, got.shape[-1]), N)
+    counts = np.bincount(states_to_numbers(x), minlength=2 ** N)
+    pe = exact_distribution(make_logfun(p), N)
+    keep = pe * counts.sum() > 50
+    z = _z_scores(counts, pe, inflate=6.0)
+    assert np.max(np.abs(z[keep])) < 5.0, np.max(np.abs(z[keep]))
+    assert 0.05 < nacc / (n_chains * (cl + 30) * N) <= 1.0
