@@ -539,7 +539,7 @@ def run_b200(args):
             "e2e": {"value": eng.S_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp32", "kernel": "sample_ratio_lean_kernel", "achieved": achieved / 1e9,
+            "roofline": {"bound": "fp32", "kernel": "sample_ratio_lean_hw_kernel", "achieved": achieved / 1e9,
                          "peak": peak / 1e9, "unit": "G hidden-unit updates/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "note": (f"the dominant kernel is bound by the FP32 pipe, neither HBM nor tensor: algorithmic work = "

@@ -10,7 +10,7 @@ namespace nkfb {
 bool ratio_hw_supported(int NP16) { return NP16 >= 11 && NP16 <= 16; }
 
 template <int NP>
-static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_one, cudaStream_t st) {
+static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_one, int warps, cudaStream_t st) {
 #ifdef NKFB_TUNE
   if (const char *v = getenv("NKFB_HW_VARIANT")) {
     if (!gl_one) switch (atoi(v)) {
@@ -19,14 +19,20 @@ static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int 
       case 3: return launch_ratio_lean_hw<NP, 4, 4, 16, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
       case 4: return launch_ratio_lean_hw<NP, 4, 4, 16, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
       case 5: return launch_ratio_lean_hw<NP, 4, 1, 16, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 6: return launch_ratio_lean_hw<NP, 4, 4, 20, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 7: return launch_ratio_lean_hw<NP, 4, 4, 20, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 8: return launch_ratio_lean_hw<NP, 4, 4, 24, 2>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 9: return launch_ratio_lean_hw<NP, 4, 4, 24, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 10: return launch_ratio_lean_hw<NP, 4, 2, 20, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-      case 11: return launch_ratio_lean_hw<NP, 4, 2, 24, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
       default: break;
     }
+  }
+#endif
+  // 16-warp CTAs only.  Measured on the 8-GPU shard of C4 (2048 chains; profiles/r02_sampler_notes.md, hw_check4/5.log):
+  // 16 warps 5.15 ms; 14-warp CTAs of 28 chains (74 CTAs instead of 64) 6.66 ms; 16-warp CTAs of which 14 carry chains
+  // (`warps` = 114) 6.62 ms; of which 12 carry chains (3 per sub-partition, `warps` = 112) 5.38 ms.  Fewer warps never
+  // shorten the step and an uneven 4/4/3/3 split costs 29 %, so a shard below one wave keeps full CTAs on fewer SMs.
+#ifdef NKFB_TUNE
+  if (warps == 114) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 14>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  if (warps == 112) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 12>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  if (warps == 14) {
+    if (gl_one) return launch_ratio_lean_hw<NP, 1, 4, 14>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+    return launch_ratio_lean_hw<NP, 4, 4, 14>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   }
 #endif
   if (gl_one) return launch_ratio_lean_hw<NP, 1, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
@@ -34,16 +40,17 @@ static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int 
 }
 
 // gl_one = 0: one logarithm per 4 pairs;  gl_one = 1: one logarithm per pair (wider range of X)
-int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, cudaStream_t st) {
+int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, int warps,
+                          cudaStream_t st) {
   switch (NP16) {
 #ifndef NKFB_HW_ONLY13
-    case 11: return go_hw<11>(h, net, a, gl_one, st);
-    case 12: return go_hw<12>(h, net, a, gl_one, st);
-    case 14: return go_hw<14>(h, net, a, gl_one, st);
-    case 15: return go_hw<15>(h, net, a, gl_one, st);
-    case 16: return go_hw<16>(h, net, a, gl_one, st);
+    case 11: return go_hw<11>(h, net, a, gl_one, warps, st);
+    case 12: return go_hw<12>(h, net, a, gl_one, warps, st);
+    case 14: return go_hw<14>(h, net, a, gl_one, warps, st);
+    case 15: return go_hw<15>(h, net, a, gl_one, warps, st);
+    case 16: return go_hw<16>(h, net, a, gl_one, warps, st);
 #endif
-    case 13: return go_hw<13>(h, net, a, gl_one, st);
+    case 13: return go_hw<13>(h, net, a, gl_one, warps, st);
     default: break;
   }
   NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "half-warp sampler: %d unit pairs per lane is not instantiated", NP16);

@@ -67,7 +67,9 @@ inline size_t lean_hw_smem_bytes(int NP, int W, int W32) {
 
 // NP pairs of units per lane (M <= 32 NP); GL pairs per logarithm; UNR unroll factor of the steps of a chunk;
 // W_ warps per CTA (= rows of a chunk: one bulk copy per warp); SG pairs whose row entries are in registers at a time
-template <int NP, int GL, int UNR, int W_, int SG>
+// WA <= W_ warps of the CTA carry chains; the others exit at once (a CTA of fewer chains whose warps are still laid
+// out like those of a 16-warp CTA)
+template <int NP, int GL, int UNR, int W_, int SG, int WA = W_>
 __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev<float> net, const float *ws, const float s0,
                                                                   const float s1, SampArgs a, const int *site_seq,
                                                                   const float *a0_seq) {
@@ -81,9 +83,9 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   samp_resolve_offset(a);
   const int N = net.N, M = net.M, W32 = (N + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int W = W_;
+  constexpr int W = WA;
   const int hl = lane & 15, hc = lane >> 4;  // lane within the half warp; chain slot of this half
-  static_assert(W_ >= 2 * LEAN_T, "TMA staging: one row of a chunk per warp (warps beyond 2 T request none)");
+  static_assert(W_ >= 8 && W_ <= 32, "warps per CTA");
   float *rows = reinterpret_cast<float *>(lean_hw_smem);                          // [3][T][2][ROW]
   int4 *steptab = reinterpret_cast<int4 *>(rows + (size_t)3 * 2 * T * ROW);       // [3][T]
   const int CB = SB + ((W32 + 3) & ~3);                                          // ints per chain block
@@ -99,11 +101,12 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
       lean_mbar_init(bar_full + 8 * b, 2 * LEAN_T);  // one arrive.expect_tx per row of the chunk
-      lean_mbar_init(bar_empty + 8 * b, W_);         // one arrive per warp
+      lean_mbar_init(bar_empty + 8 * b, WA);         // one arrive per warp that carries chains
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (WA < W_ && warp >= WA) return;
   const int64_t chain0 = ((int64_t)blockIdx.x * W + warp) * C;
   const V one = P::mk(1.0f, 1.0f);
   const int n_valid = a.n_chains - chain0 >= C ? C : (a.n_chains > chain0 ? (int)(a.n_chains - chain0) : 0);
@@ -158,12 +161,8 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   // one bulk copy; warp 0 also writes the step table before its arrive (release) on the buffer's full barrier.
   // Table entry: byte offset of the configuration word inside the chain block, bit mask, A_site in fixed point.
   auto issue_rows_tma = [&](uint32_t j, uint32_t b) {
-    if (W_ > 2 * T && warp >= 2 * T) return;
-    const int tt = warp >> 1, tab = warp & 1;
     const int pos = (int)((q0c + j) << LEAN_TSH) - (int)phase;   // step index of the chunk's first slot
     const int last = (int)n_steps - 1;
-    const int sc = min(max(pos + tt, 0), last);
-    const int st = __ldg(site_seq + sc);
     if (warp == 0 && lane < T) {
       const int scl = min(max(pos + lane, 0), last);
       const int stl = __ldg(site_seq + scl);
@@ -171,10 +170,16 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
                                         __float2int_rn(__ldg(a0_seq + scl) * LEAN_FT), stl);
     }
     __syncwarp();
-    if (lane == 0) {
-      const uint32_t dst = rows_addr + (uint32_t)(((b * T + tt) * 2 + tab) * (ROW * 4));
-      lean_mbar_arrive_expect_tx(bar_full + 8 * b, (uint32_t)(ROW * sizeof(float)));
-      lean_bulk_g2s(dst, ws + (size_t)(tab * N + st) * ROW, (uint32_t)(ROW * sizeof(float)), bar_full + 8 * b);
+    // row r = (step r / 2, table r % 2) of the chunk: one bulk copy each, dealt to the warps (W_ = 2 T: one per warp)
+#pragma unroll
+    for (int r = warp; r < 2 * T; r += WA) {
+      const int tt = r >> 1, tab = r & 1;
+      const int st = __ldg(site_seq + min(max(pos + tt, 0), last));
+      if (lane == 0) {
+        const uint32_t dst = rows_addr + (uint32_t)(((b * T + tt) * 2 + tab) * (ROW * 4));
+        lean_mbar_arrive_expect_tx(bar_full + 8 * b, (uint32_t)(ROW * sizeof(float)));
+        lean_bulk_g2s(dst, ws + (size_t)(tab * N + st) * ROW, (uint32_t)(ROW * sizeof(float)), bar_full + 8 * b);
+      }
     }
   };
 
@@ -410,15 +415,15 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   if (a.n_accepted && hl == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-template <int NP, int GL, int UNR = 4, int W_ = 16, int SG = 2>
+template <int NP, int GL, int UNR = 4, int W_ = 16, int SG = 2, int WA = W_>
 static int launch_ratio_lean_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws16,
                                 const int *site_seq, const float *a0_seq, cudaStream_t st) {
   const size_t smem = lean_hw_smem_bytes(NP, W_, (net->n_visible + 31) >> 5);
-  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG>,
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
-  const int64_t blocks = (a.n_chains + (int64_t)2 * W_ - 1) / ((int64_t)2 * W_);
-  sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG><<<(unsigned)blocks, W_ * 32, smem, st>>>(
+  const int64_t blocks = (a.n_chains + (int64_t)2 * WA - 1) / ((int64_t)2 * WA);
+  sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA><<<(unsigned)blocks, W_ * 32, smem, st>>>(
       make_netdev<float>(net), (const float *)ws16, (float)a.s0, (float)a.s1, a, site_seq, a0_seq);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

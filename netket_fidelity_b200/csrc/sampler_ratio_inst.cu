@@ -12,7 +12,8 @@
 namespace nkfb {
 
 // half-warp lean kernel (sampler_hw_inst.cu): a.ws_hw = q tables in the 16-lane layout, a.np_hw pairs per lane
-int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, cudaStream_t st);
+int dispatch_ratio_hw_f32(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int NP16, int gl_one, int warps,
+                          cudaStream_t st);
 
 #define NKFB_CAT_(a, b, c) a##b##_L##c
 #define NKFB_CAT(a, b, c) NKFB_CAT_(a, b, c)
@@ -114,8 +115,13 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
         // default: rows staged by the TMA unit with an mbarrier pipeline (sampler_lean_tma.cuh, 21.8 ms per launch at
         // C4); NKFB_LEAN_TMA=0: the cp.async form (sampler_lean.cuh, 22.6 ms)
         const char *tma = getenv("NKFB_LEAN_TMA");
-        if (lean && a.ws_hw != nullptr)
-          rc = dispatch_ratio_hw_f32(h, net, ah, a.np_hw, gl_one, st);
+        if (lean && a.ws_hw != nullptr) {
+          // 14-warp CTAs for launches below one wave (tuning builds only: measured slower, sampler_hw_inst.cu)
+          int warps = 16;
+          if (getenv("NKFB_HW_W14") && head == a.n_chains && blocks < slots && (head + 27) / 28 <= slots)
+            warps = atoi(getenv("NKFB_HW_W14"));
+          rc = dispatch_ratio_hw_f32(h, net, ah, a.np_hw, gl_one, warps, st);
+        }
         else if (lean && !(tma && atoi(tma) == 0))
           rc = gl_one ? launch_ratio_lean_tma<NP, 2, 1, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st)
                       : launch_ratio_lean_tma<NP, 2, GW, 4>(h, net, ah, ws, a.site_seq, (const float *)a.a0_seq, st);
