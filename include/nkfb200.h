@@ -92,7 +92,7 @@ typedef struct {
   uint64_t step_offset;  /* MH steps already consumed by earlier calls (Philox counter offset) */
   double local_states[2];
   int32_t init_random;   /* !=0: ignore chain_state on input, start from Philox-random configurations */
-  int32_t reserved;
+  int32_t flags;         /* NKFB_SAMPLE_* bits (0 = none; was `reserved`) */
   void *workspace;         /* device scratch of >= nkfb_sample_workspace_bytes() bytes, or NULL to use the
                               handle's own buffer (then calls on different streams must not overlap) */
   uint64_t workspace_bytes;
@@ -120,7 +120,13 @@ int64_t nkfb_launch_count(nkfb_handle_t h);
 /* NKFB_OPT_SAMPLER_SHARE (default 1): how many nkfb_sample launches of equal size the caller runs side by side
  * on different streams (2 for the two chain families of an infidelity step).  Only a scheduling hint: it decides
  * whether the chains beyond the last full wave of CTAs are handed to the one-chain-per-warp kernel. */
-enum { NKFB_OPT_SAMPLER_ALGO = 1, NKFB_OPT_SAMPLER_SHARE = 2 };
+/* NKFB_OPT_FWD_MAX_CTAS (default 0 = no limit): upper bound on the CTAs of the next nkfb_infidelity_fwd launches.  Lets a
+ * caller run pass A on the SMs a concurrent sub-wave sampler launch leaves idle (engine.py, streamed segments). */
+enum { NKFB_OPT_SAMPLER_ALGO = 1, NKFB_OPT_SAMPLER_SHARE = 2, NKFB_OPT_FWD_MAX_CTAS = 3 };
+/* nkfb_sample_cfg_t.flags.  NKFB_SAMPLE_TABLES_VALID: `workspace` (caller-provided) still holds the parameter tables an
+ * earlier nkfb_sample call wrote for the SAME net, local_states and plain target; their preparation kernels are skipped
+ * (a chain sampled in several consecutive calls between two parameter updates).  Ignored for composite targets. */
+enum { NKFB_SAMPLE_TABLES_VALID = 1 };
 int nkfb_set_option(nkfb_handle_t h, int key, int64_t value);
 
 /* ---- configurations <-> packed bits ------------------------------------- */

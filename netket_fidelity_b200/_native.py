@@ -28,6 +28,7 @@ SYMBOLS = [
 
 OPT_SAMPLER_ALGO = 1
 OPT_SAMPLER_SHARE = 2
+OPT_FWD_MAX_CTAS = 3
 SAMPLER_AUTO, SAMPLER_ADDITIVE, SAMPLER_MULTIPLICATIVE = 0, 1, 2
 
 
@@ -51,7 +52,7 @@ class SampleCfgT(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("chain_length", C.c_int32), ("n_discard", C.c_int32),
                 ("sweep_size", C.c_int32), ("site_mode", C.c_int32), ("seed", C.c_uint64),
                 ("chain_offset", C.c_uint64), ("step_offset", C.c_uint64),
-                ("local_states", C.c_double * 2), ("init_random", C.c_int32), ("reserved", C.c_int32),
+                ("local_states", C.c_double * 2), ("init_random", C.c_int32), ("flags", C.c_int32),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
                 ("step_offset_dev", C.c_void_p)]
 
@@ -254,6 +255,10 @@ class Handle:
         chain families of a step: 2); see include/nkfb200.h."""
         self.set_option(OPT_SAMPLER_SHARE, n)
 
+    def set_fwd_max_ctas(self, n):
+        """Upper bound on the CTAs of the next tensor-core estimator launches (0: no limit); include/nkfb200.h."""
+        self.set_option(OPT_FWD_MAX_CTAS, n)
+
     # ---------------------------------------------------------------- pack / unpack
     def pack(self, x, local_states):
         x = x.contiguous()
@@ -298,8 +303,9 @@ class Handle:
     # ---------------------------------------------------------------- sampler
     def sample(self, net: RbmSpec, chain_state, chain_length, n_discard, sweep_size, seed, local_states,
                op: OpSpec | None = None, chain_offset=0, step_offset=0, site_mode=0, init_random=False,
-               n_accepted=None, out=None, workspace=None, step_offset_dev=None):
-        """step_offset_dev: optional device int64[1] added to step_offset by the kernels (CUDA-graph replays)."""
+               n_accepted=None, out=None, workspace=None, step_offset_dev=None, tables_valid=False):
+        """step_offset_dev: optional device int64[1] added to step_offset by the kernels (CUDA-graph replays).
+        tables_valid: `workspace` still holds the tables an earlier call wrote for the same net (NKFB_SAMPLE_TABLES_VALID)."""
         n_chains, W32 = chain_state.shape
         self._on_device(net.kernel, chain_state, out, n_accepted, workspace, step_offset_dev)
         if out is None:
@@ -310,6 +316,7 @@ class Handle:
         cfg.chain_offset, cfg.step_offset = int(chain_offset), int(step_offset)
         cfg.local_states = _ls(local_states)
         cfg.init_random = 1 if init_random else 0
+        cfg.flags = 1 if (tables_valid and workspace is not None) else 0
         if workspace is not None:
             cfg.workspace = workspace.data_ptr()
             cfg.workspace_bytes = workspace.numel() * workspace.element_size()
@@ -329,14 +336,24 @@ class Handle:
 
     # ---------------------------------------------------------------- estimator / gradient
     def infidelity_fwd(self, psi: RbmSpec, phi: RbmSpec, sigma, eta, local_states, cv_coeff, op1=None, op2=None,
-                       op4=None, sums=None):
+                       op4=None, sums=None, out=None):
+        """out: optional (log_val, L, rho1) buffers of S entries each (slices of larger arrays when pass A runs segment by
+        segment); the sums are ACCUMULATED into `sums`."""
         S = sigma.shape[0]
         dev = sigma.device
         self._on_device(psi.kernel, phi.kernel, sigma, eta, sums)
         cd, rd = psi.kernel.dtype, real_dtype(psi.code)
-        log_val = torch.empty((S,), dtype=cd, device=dev)
-        L = torch.empty((S,), dtype=rd, device=dev)
-        rho1 = torch.empty((S,), dtype=cd, device=dev)
+        if out is not None:
+            log_val, L, rho1 = out
+            self._on_device(log_val, L, rho1)
+            if not (log_val.is_contiguous() and L.is_contiguous() and rho1.is_contiguous()) or \
+                    (log_val.shape[0], L.shape[0], rho1.shape[0]) != (S, S, S) or \
+                    (log_val.dtype, L.dtype, rho1.dtype) != (cd, rd, cd):
+                raise ValueError("infidelity_fwd: out buffers must be contiguous (S,) arrays of the state's dtypes")
+        else:
+            log_val = torch.empty((S,), dtype=cd, device=dev)
+            L = torch.empty((S,), dtype=rd, device=dev)
+            rho1 = torch.empty((S,), dtype=cd, device=dev)
         if sums is None:
             sums = torch.zeros((8,), dtype=torch.float64, device=dev)
         a, b = psi.struct(), phi.struct()

@@ -347,6 +347,10 @@ extern "C" int nkfb_set_option(nkfb_handle_t h, int key, int64_t value) {
       if (value < 1 || value > 16) NKFB_FAIL(h, NKFB_ERR_INVALID, "sampler share must be in 1..16");
       h->opt_sampler_share = (int)value;
       return NKFB_OK;
+    case NKFB_OPT_FWD_MAX_CTAS:
+      if (value < 0 || value > (1 << 20)) NKFB_FAIL(h, NKFB_ERR_INVALID, "estimator CTA limit must be >= 0");
+      h->opt_fwd_max_ctas = (int)value;
+      return NKFB_OK;
     default: NKFB_FAIL(h, NKFB_ERR_INVALID, "unknown option %d", key);
   }
 }

@@ -24,6 +24,7 @@ struct nkfb_handle_s {
   size_t ws4_bytes;
   int opt_sampler_algo;  // NKFB_OPT_SAMPLER_ALGO
   int opt_sampler_share; // NKFB_OPT_SAMPLER_SHARE: sampler launches of equal size that run side by side (default 1)
+  int opt_fwd_max_ctas;  // NKFB_OPT_FWD_MAX_CTAS: upper bound on the CTAs of the tensor-core estimator (0 = none)
 };
 
 // Every entry point runs on the handle's device whatever the caller's current device is, and restores the latter.

@@ -503,7 +503,8 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   a.n_groups = (tiles + TC_T - 1) / TC_T;
   a.tmem_cols = smem > (size_t)115 * 1024 ? 512 : 256;  // more than half of the SM's shared memory: one CTA per SM
   const int per_sm = smem <= 112 * 1024 ? 2 : 1;
-  const int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);
+  int grid = (int)std::min<int64_t>(a.n_groups, (int64_t)h->sm_count * per_sm);
+  if (h->opt_fwd_max_ctas > 0) grid = std::min(grid, h->opt_fwd_max_ctas);  // NKFB_OPT_FWD_MAX_CTAS
   // which evaluations go through a gate: bit 0 (psi, eta) U2, bit 1 (phi, sigma) U1, bit 2 (phi, eta) U4
   const int fm = (a.op2.kind == NKFB_OP_GATE ? 1 : 0) | (a.op1.kind == NKFB_OP_GATE ? 2 : 0) | (a.op4.kind == NKFB_OP_GATE ? 4 : 0);
 #define NKFB_FWD_TC_CASE(FM)                                                                                              \

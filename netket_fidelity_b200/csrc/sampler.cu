@@ -290,9 +290,9 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
   const int L = bestL, NP = ratio_pairs(M, L);
   const size_t a0_off = ratio_a0_off(N, M, L), b_off = ratio_bound_off(N, M, L);
   const size_t rsz = f32 ? 4 : 8;
-  NKFB_CHECK_CUDA(h, cudaMemsetAsync((char *)ws + b_off * rsz, 0, rsz, st));
-  {
-    const int64_t tot = (int64_t)2 * N * NP * L + N + M;
+  if (!a.tables_valid) {
+    NKFB_CHECK_CUDA(h, cudaMemsetAsync((char *)ws + b_off * rsz, 0, rsz, st));
+    const int64_t tot = (((int64_t)2 * N * NP * L + 31) & ~(int64_t)31) + (int64_t)(N + M) * 32;
     const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
     if (f32)
       prep_ratio_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), (float *)ws, L, NP, (float)a.s0,
@@ -324,11 +324,13 @@ static int dispatch_ratio(nkfb_handle_t h, const nkfb_rbm_t *net, SampArgs a, vo
     const int NP16 = ratio_pairs(M, 16);
     if (f32 && NP >= 6 && ratio_hw_supported(NP16) && !getenv("NKFB_NOHW")) {
       float *ws16 = (float *)ws + hw_ws_offset_reals(N, M);
-      const int64_t tot = (int64_t)2 * N * NP16 * 16;   // tables only: A_i and the range bound come from the 32-lane copy
-      const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
-      prep_ratio_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), ws16, 16, NP16, (float)a.s0, (float)a.s1,
-                                                     (size_t)0, (size_t)0, /*tables_only=*/1);
-      NKFB_LAUNCHED(h);
+      if (!a.tables_valid) {
+        const int64_t tot = (int64_t)2 * N * NP16 * 16;   // tables only: A_i and the range bound come from the 32-lane copy
+        const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+        prep_ratio_params<float><<<grid, 256, 0, st>>>(make_netdev<float>(net), ws16, 16, NP16, (float)a.s0, (float)a.s1,
+                                                       (size_t)0, (size_t)0, /*tables_only=*/1);
+        NKFB_LAUNCHED(h);
+      }
       a.ws_hw = ws16;
       a.np_hw = NP16;
     }
@@ -389,7 +391,7 @@ static int dispatch_plain(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs
     }
   }
   ws = (char *)ws + plain_ws_offset_reals(N, M) * (net->dtype == NKFB_F32 ? 4 : 8);
-  {
+  if (!a.tables_valid) {
     const int64_t tot = (int64_t)N * M + M + N;
     const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
     if (net->dtype == NKFB_F32)
@@ -536,6 +538,8 @@ extern "C" int nkfb_sample(nkfb_handle_t h, const nkfb_rbm_t *net, const nkfb_op
   a.op = make_opdev(op);
   cudaStream_t st = (cudaStream_t)stream;
   const bool composite = op && op->kind != NKFB_OP_NONE;
+  // tables of an earlier call: only with a caller-provided workspace (the handle's own buffer may have been reused)
+  a.tables_valid = (cfg->flags & NKFB_SAMPLE_TABLES_VALID) && cfg->workspace != nullptr && !composite;
   if ((uint64_t)(cfg->n_discard + (int64_t)cfg->chain_length) * (uint64_t)cfg->sweep_size >= (1ull << 31))
     NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "more than 2^31 Metropolis steps in one call");
   if (!composite) return dispatch_plain(h, net, a, cfg->workspace, (size_t)cfg->workspace_bytes, st);

@@ -29,6 +29,7 @@ struct SampArgs {
   // q tables in the 16-lane layout for the half-warp kernel (sampler_lean_hw.cuh), np_hw pairs per lane; or null
   const void *ws_hw;
   int np_hw;
+  int tables_valid;  // host side only: the workspace already holds this net's tables (NKFB_SAMPLE_TABLES_VALID)
   OpDev op;
 };
 

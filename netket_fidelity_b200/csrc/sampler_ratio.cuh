@@ -80,7 +80,12 @@ __global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s
   const int64_t slots_per_tab = (int64_t)N * NP * L;
   const int64_t n_slots = 2 * slots_per_tab;
   const double dx = (double)s1 - (double)s0;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_slots + (tables_only ? 0 : N + M);
+  // the N + M reductions (A_i over the hidden units, the range bound over the sites) take one WARP each: one thread each
+  // made this kernel 29 us long (400 dependent loads), on the critical path of every sampler launch
+  // (the reduction items start at a warp boundary: a warp is either all table slots or all lanes of one item)
+  const int64_t red0 = (n_slots + 31) & ~(int64_t)31;
+  const int64_t n_red = tables_only ? 0 : (int64_t)(N + M) * 32;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < red0 + n_red;
        idx += (int64_t)gridDim.x * blockDim.x) {
     if (idx < n_slots) {
       const int tab = idx >= slots_per_tab;
@@ -106,20 +111,30 @@ __global__ void prep_ratio_params(NetDev<R> net, R *ws, int L, int NP, R s0, R s
         out[2 + u] = qi;
       }
       st4(ws + 4 * idx, out);
-    } else if (idx < n_slots + N) {
-      const int i = (int)(idx - n_slots);
-      double acc = net.a ? (double)net.a[2 * i] : 0.0;
-      for (int j = 0; j < M; ++j) acc += (double)net.W[2 * ((int64_t)i * M + j)];
-      ws[a0_off + i] = (R)(2.0 * LOG2E * dx * acc);
-    } else {
-      const int j = (int)(idx - n_slots - N);
-      const double smax = fmax(fabs((double)s0), fabs((double)s1));
-      double acc = 0.0;
-      for (int i = 0; i < N; ++i) acc += fabs((double)net.W[2 * ((int64_t)i * M + j)]);
-      acc = acc * smax + (net.b ? fabs((double)net.b[2 * j]) : 0.0);
-      float xb = __double2float_ru(acc);
-      if (!(xb == xb)) xb = __int_as_float(0x7f800000);  // NaN parameters -> no fast path
-      atomicMax(reinterpret_cast<unsigned int *>(ws + bound_off), __float_as_uint(xb));  // xb >= 0: bit order = value order
+    } else if (idx >= red0) {
+      const int64_t item = (idx - red0) >> 5;
+      const int ln = (int)((idx - red0) & 31);
+      if (item < N) {
+        const int i = (int)item;
+        double acc = 0.0;
+        for (int j = ln; j < M; j += 32) acc += (double)net.W[2 * ((int64_t)i * M + j)];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (ln == 0) ws[a0_off + i] = (R)(2.0 * LOG2E * dx * (acc + (net.a ? (double)net.a[2 * i] : 0.0)));
+      } else {
+        const int j = (int)(item - N);
+        const double smax = fmax(fabs((double)s0), fabs((double)s1));
+        double acc = 0.0;
+        for (int i = ln; i < N; i += 32) acc += fabs((double)net.W[2 * ((int64_t)i * M + j)]);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (ln == 0) {
+          acc = acc * smax + (net.b ? fabs((double)net.b[2 * j]) : 0.0);
+          float xb = __double2float_ru(acc);
+          if (!(xb == xb)) xb = __int_as_float(0x7f800000);  // NaN parameters -> no fast path
+          atomicMax(reinterpret_cast<unsigned int *>(ws + bound_off), __float_as_uint(xb));  // xb >= 0: bit order = value order
+        }
+      }
     }
   }
 }

@@ -79,7 +79,25 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar) {
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
+// NKFB_MBAR_HINT (ns): upper bound of the time a try_wait may stay suspended before it returns false; the default
+// interval made the waiting epilogue warps poll (SYNCS + YIELD + BRA were a fifth of the executed instructions)
+#ifndef NKFB_MBAR_HINT
+#define NKFB_MBAR_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+#if NKFB_MBAR_HINT > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(mbar),
+      "r"(parity), "r"((uint32_t)NKFB_MBAR_HINT)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -91,6 +109,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       "}\n" ::"r"(mbar),
       "r"(parity)
       : "memory");
+#endif
 }
 // the same wait for a warp that has nothing else to do (the UMMA-issuing warp): sleep between polls so that its spin
 // does not take issue slots from the epilogue warps of its sub-partition (a tight try_wait loop ran at 0.22 IPC)

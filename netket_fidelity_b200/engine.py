@@ -29,7 +29,7 @@ from . import parallel as par
 
 class StepConfig:
     def __init__(self, n_chains, chain_length, n_discard, sweep_size=None, seed=0, local_states=(-1.0, 1.0),
-                 cv_coeff=-0.5, site_mode=0, one_collective=False):
+                 cv_coeff=-0.5, site_mode=0, one_collective=False, stream_segments=None):
         self.n_chains = int(n_chains)            # GLOBAL number of chains per family
         self.chain_length = int(chain_length)
         self.n_discard = int(n_discard)
@@ -41,6 +41,10 @@ class StepConfig:
         # one all-reduce per step instead of two: pass B is centred with the PREVIOUS step's F and an
         # extra accumulator sum_s conj O_k(sigma_s) makes the result exact; costs the sigma half of pass B once more
         self.one_collective = bool(one_collective)
+        # pass A streamed under the sampler: the chains are sampled in K consecutive segments and pass A of segment k
+        # runs, on the SMs a sub-wave sampler launch leaves idle, while segment k + 1 is being sampled.
+        # None: automatic (2 when the shard's sampler launches leave >= 16 SMs idle -- the 8-GPU shard of C4), 1: off
+        self.stream_segments = stream_segments
 
 
 class InfidelityStep:
@@ -75,9 +79,22 @@ class InfidelityStep:
         dev = self.dev
         self.state_psi = torch.zeros((self.local_chains, W32), dtype=torch.int32, device=dev)
         self.state_phi = torch.zeros((self.local_chains, W32), dtype=torch.int32, device=dev)
-        self.sigma = torch.empty((self.local_chains, cfg.chain_length, W32), dtype=torch.int32, device=dev)
-        self.eta = torch.empty_like(self.sigma)
         self.S_local = self.local_chains * cfg.chain_length
+        self.K = self._pick_segments()
+        if self.K > 1:
+            # segment-major samples: [segment][chain][sample within the segment]; pass A / pass B see flat lists
+            self.sigma = torch.empty((self.K, self.local_chains, cfg.chain_length // self.K, W32), dtype=torch.int32,
+                                     device=dev)
+            self.psi_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.est_stream = torch.cuda.Stream(device=dev, priority=0)
+            self._lv = torch.empty((self.S_local,), dtype=cdtype, device=dev)
+            self._rho1 = torch.empty((self.S_local,), dtype=cdtype, device=dev)
+            self._L = torch.empty((self.S_local,), dtype=torch.float32 if cdtype == torch.complex64 else torch.float64,
+                                  device=dev)
+        else:
+            self.sigma = torch.empty((self.local_chains, cfg.chain_length, W32), dtype=torch.int32, device=dev)
+        self.eta = torch.empty_like(self.sigma)
+        self._passA_done = False
         self.S_total = cfg.n_chains * cfg.chain_length
         P = N * M + M + N
         self.P = P
@@ -93,7 +110,7 @@ class InfidelityStep:
         self.n_accepted = torch.zeros((2,), dtype=torch.int64, device=dev)
         # the two chain families are sampled on two streams so that the tail of one launch (a partial last
         # wave of CTAs) overlaps the other launch; each has its own scratch for the pre-scaled parameters
-        self.side_stream = torch.cuda.Stream(device=dev)
+        self.side_stream = torch.cuda.Stream(device=dev, priority=-1 if self.K > 1 else 0)
         self.single_stream = os.environ.get("NKFB_SINGLE_STREAM", "0") == "1"
         self.ws_psi = self.ws_phi = None
         self.steps_done = 0
@@ -106,7 +123,84 @@ class InfidelityStep:
         self.last = {}
 
     # ------------------------------------------------------------------
+    def _pick_segments(self):
+        cfg = self.cfg
+        K = cfg.stream_segments
+        if os.environ.get("NKFB_STREAM_SEGMENTS"):
+            K = int(os.environ["NKFB_STREAM_SEGMENTS"])
+        if cfg.one_collective:
+            return 1
+        if K is None:
+            # automatic: single precision, the shape range of the CTA-synchronous samplers (32 chains per CTA), both
+            # launches together leave >= 16 SMs idle, segments large enough for the tensor-core estimator
+            sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            ctas = 2 * ((self.local_chains + 31) // 32)
+            ok = (self.cdtype == torch.complex64 and 161 <= self.M <= 512 and self.N <= 128 and cfg.site_mode == 0
+                  and self.local_chains >= 1024 and ctas <= sm - 16 and cfg.chain_length % 2 == 0
+                  and self.S_local // 2 >= 2048)
+            # two segments: every further one costs ~0.1 ms of pipeline start-up and straggler wait per sampler launch
+            # (measured on the 8-GPU shard of C4: K = 1 / 2 / 4 / 8 -> 6.40 / 6.29 / 6.41 / 6.75 ms per step)
+            K = 2 if ok else 1
+        K = max(1, int(K))
+        if K > 1 and cfg.chain_length % K != 0:
+            raise ValueError(f"stream_segments = {K} does not divide chain_length = {cfg.chain_length}")
+        return K
+
+    def _sample_streamed(self, psi: nv.RbmSpec, phi: nv.RbmSpec):
+        """K segments of chain_length / K samples per chain; the two families of a segment on two high-priority streams,
+        pass A of segment k on a low-priority stream behind both (its CTAs limited to the SMs the samplers leave idle),
+        concurrent with the sampling of segment k + 1.  Chains continue from segment to segment exactly as they continue
+        from call to call (device-resident configurations, Philox counters keyed by the absolute step)."""
+        cfg, K = self.cfg, self.K
+        seg = cfg.chain_length // K
+        S_seg = self.local_chains * seg
+        init = not self.initialised
+        steps_per_call = (cfg.n_discard + cfg.chain_length) * self.sweep
+        base = self.steps_done * steps_per_call
+        if self.ws_psi is None:
+            self.ws_psi, self.ws_phi = self.h.sample_workspace(psi), self.h.sample_workspace(phi)
+        main = torch.cuda.current_stream(self.dev)
+        self.acc.zero_()
+        for st in (self.psi_stream, self.side_stream, self.est_stream):
+            st.wait_stream(main)
+        sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        idle = max(1, sm - 2 * ((self.local_chains + 31) // 32))
+        self.h.set_sampler_share(2)
+        try:
+            for k in range(K):
+                nd = cfg.n_discard if k == 0 else 0
+                off = base + (0 if k == 0 else (cfg.n_discard + k * seg) * self.sweep)
+                with torch.cuda.stream(self.psi_stream):
+                    self.h.sample(psi, self.state_psi, seg, nd, self.sweep, cfg.seed, cfg.local_states, op=None,
+                                  chain_offset=self.chain_offset, step_offset=off, site_mode=cfg.site_mode,
+                                  init_random=init and k == 0, n_accepted=self.n_accepted[0:1], out=self.sigma[k],
+                                  workspace=self.ws_psi, tables_valid=k > 0)
+                with torch.cuda.stream(self.side_stream):
+                    self.h.sample(phi, self.state_phi, seg, nd, self.sweep, cfg.seed, cfg.local_states,
+                                  op=self.op_target, chain_offset=cfg.n_chains + self.chain_offset, step_offset=off,
+                                  site_mode=cfg.site_mode, init_random=init and k == 0,
+                                  n_accepted=self.n_accepted[1:2], out=self.eta[k], workspace=self.ws_phi,
+                                  tables_valid=k > 0)
+                self.est_stream.wait_stream(self.psi_stream)
+                self.est_stream.wait_stream(self.side_stream)
+                with torch.cuda.stream(self.est_stream):
+                    # two estimator CTAs per idle SM while a sampler segment is still to come; the last one has the GPU
+                    self.h.set_fwd_max_ctas(2 * idle if k < K - 1 else 0)
+                    sl = slice(k * S_seg, (k + 1) * S_seg)
+                    self.h.infidelity_fwd(psi, phi, self.sigma[k].view(-1, self.W32), self.eta[k].view(-1, self.W32),
+                                          cfg.local_states, cfg.cv_coeff, self.op1, self.op2, self.op4, sums=self.sums,
+                                          out=(self._lv[sl], self._L[sl], self._rho1[sl]))
+        finally:
+            self.h.set_sampler_share(1)
+            self.h.set_fwd_max_ctas(0)
+        main.wait_stream(self.est_stream)
+        self._passA_done = True
+        self.initialised = True
+        self.steps_done += 1
+
     def sample(self, psi: nv.RbmSpec, phi: nv.RbmSpec):
+        if self.K > 1 and self._step_dev is None:
+            return self._sample_streamed(psi, phi)
         cfg = self.cfg
         init = not self.initialised
         steps_per_call = (cfg.n_discard + cfg.chain_length) * self.sweep
@@ -151,13 +245,21 @@ class InfidelityStep:
         eta = self.eta.view(-1, self.W32)
         if cfg.one_collective and return_grad:
             return self._estimate_one_collective(psi, phi, sig, eta, events)
-        self.acc.zero_()
-        if events:
-            events[0].record()
-        log_val, L, rho1, _ = self.h.infidelity_fwd(psi, phi, sig, eta, cfg.local_states, cfg.cv_coeff, self.op1,
-                                                    self.op2, self.op4, sums=self.sums)
-        if events:
-            events[1].record()
+        if self._passA_done:
+            # pass A ran segment by segment under the sampler (_sample_streamed); its sums are in self.sums
+            self._passA_done = False
+            log_val, L, rho1 = self._lv, self._L, self._rho1
+            if events:
+                events[0].record()
+                events[1].record()
+        else:
+            self.acc.zero_()
+            if events:
+                events[0].record()
+            log_val, L, rho1, _ = self.h.infidelity_fwd(psi, phi, sig, eta, cfg.local_states, cfg.cv_coeff, self.op1,
+                                                        self.op2, self.op4, sums=self.sums)
+            if events:
+                events[1].record()
         self._allreduce(self.sums)
         grad = None
         if return_grad:
@@ -215,6 +317,8 @@ class InfidelityStep:
         # tried in round 2 and hung on 2 GPUs (gpurun call 176: no progress for 15 min), so it stays refused.
         if self.world != 1:
             raise RuntimeError("capture_graph: single-rank only (capturing the NCCL all-reduces hung on 2 GPUs)")
+        if self.K > 1:
+            raise RuntimeError("capture_graph: not with streamed segments (StepConfig(stream_segments=1) turns them off)")
         if self._graph is not None:
             return
         if not self.initialised:

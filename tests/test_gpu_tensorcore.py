@@ -88,3 +88,41 @@ def test_tc_gradient_eight_and_sixteen_warp_forms_agree(h, monkeypatch, N, M, S,
         g[form] = h.grad_finalize(gacc, sums, a.n_params, torch.complex64).cpu().numpy()
         assert rel_err(g[form], ref["grad"].ravel()) <= 1e-5, (form, rel_err(g[form], ref["grad"].ravel()))
     assert rel_err(g["wide"], g["narrow"]) <= 1e-6, rel_err(g["wide"], g["narrow"])
+
+
+@pytest.mark.parametrize("B", [10.0, 100.0])
+def test_tc_estimator_large_imaginary_preactivations(h, B):
+    """Hidden biases with imaginary parts +-B, so |Im theta| ~ B (a trained complex RBM).  In single
+    precision theta itself carries an absolute error ~ 2^-24 B whatever the kernel, and the tensor-core epilogue's
+    cos.approx / sin.approx add the rounding of 2 y / (2 pi) (another ~2^-24 2B in the phase) -- both grow linearly
+    with B.  Held here: both fp32 forms stay within 4e-5 max(1, B / 4) of the complex128 oracle on the per-sample
+    estimator (1e-5-grade up to |Im theta| ~ 4, degrading in proportion beyond), and within that of each other, so the
+    switch from the CUDA-core to the tensor-core kernel at S = 2048 is not a discontinuity beyond fp32 rounding."""
+    N, M, S = 20, 40, 4096
+    rng = np.random.default_rng(3)
+    psi, phi = _net(N, M, 1234, 0.05), _net(N, M, 5678, 0.05)
+    sign = np.where(np.arange(M) % 2 == 0, 1.0, -1.0)
+    psi = RBMParams(psi.kernel, psi.bias + 1j * B * sign, psi.visible_bias)
+    phi = RBMParams(phi.kernel, phi.bias - 1j * B * sign, phi.visible_bias)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    a, b = to_rbmspec(psi, torch.complex64), to_rbmspec(phi, torch.complex64)
+    U, Ud = oops.Rx(N, 3, 0.37), oops.Rx(N, 3, -0.37)
+    U1, U2, U4 = mode_slots("upsi", U, Ud)
+    # the oracle evaluates the complex64-rounded parameters the kernels see
+    c64 = lambda p: RBMParams(p.kernel.astype(np.complex64).astype(np.complex128),
+                              p.bias.astype(np.complex64).astype(np.complex128),
+                              None if p.visible_bias is None else p.visible_bias.astype(np.complex64).astype(np.complex128))
+    ref = infidelity_and_grad(c64(psi), c64(phi), sigma, eta, -0.5, U1, U2, U4)
+    tol = 4e-5 * max(1.0, B / 4.0)   # measured at B = 10: 5.0e-5 (tensor cores)
+    out = {}
+    try:
+        for impl in ("tc", "simt"):
+            os.environ["NKFB_FWD_IMPL"] = impl
+            lv, L, rho1, sums = h.infidelity_fwd(a, b, sp, ep, LS, -0.5, to_opspec(U1), to_opspec(U2), to_opspec(U4))
+            torch.cuda.synchronize()
+            out[impl] = L.cpu().numpy()
+            assert rel_err(out[impl], ref["L"]) <= tol, (impl, B, rel_err(out[impl], ref["L"]))
+    finally:
+        os.environ.pop("NKFB_FWD_IMPL", None)
+    assert rel_err(out["tc"], out["simt"]) <= tol, rel_err(out["tc"], out["simt"])

@@ -17,7 +17,7 @@ dev = torch.device("cuda", 0)
 U, Ud = device_ops(w, dev)
 specs = {k: nv.RbmSpec(*[t.to(dev) if t is not None else None for t in random_rbm(N, M, seed, torch.complex64, w["vb"])])
          for k, seed in (("psi", 1234), ("phi", 5678))}
-flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+flush = torch.empty((160 << 20,), dtype=torch.uint8, device=dev)
 base = None
 for G in [int(g) for g in os.environ.get("SHARD_G", "1,2,4,8").split(",")]:
     cfg = StepConfig(w["n_chains"] // G, w["chain_length"], 5, N, seed=20261019, cv_coeff=-0.5)
