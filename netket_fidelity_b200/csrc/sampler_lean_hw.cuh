@@ -69,7 +69,11 @@ inline size_t lean_hw_smem_bytes(int NP, int W, int W32) {
 // W_ warps per CTA (= rows of a chunk: one bulk copy per warp); SG pairs whose row entries are in registers at a time
 // WA <= W_ warps of the CTA carry chains; the others exit at once (a CTA of fewer chains whose warps are still laid
 // out like those of a 16-warp CTA)
-template <int NP, int GL, int UNR, int W_, int SG, int WA = W_>
+// PF = 1 (experiment, off): table entry, configuration word and threshold of step t + 1 are loaded during the multiply
+// phase of step t (the word patched if step t flips a bit of the same word), which takes two dependent shared-memory
+// round trips off the critical path of a step -- measured SLOWER (5.46 vs 5.11 ms per wave with 16 warps, 3.06 vs 3.00 ms
+// with one warp per scheduler, gpurun_out/hw_check7.log): five more live registers cost more than the ~50 cycles saved.
+template <int NP, int GL, int UNR, int W_, int SG, int WA = W_, int PF = 0>
 __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev<float> net, const float *ws, const float s0,
                                                                   const float s1, SampArgs a, const int *site_seq,
                                                                   const float *a0_seq) {
@@ -302,6 +306,34 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   // ptxas pays ~27 MOVs on the ACCEPT path (95 % of the steps) to merge them; with the loop the new z always comes out
   // of the same instructions and only the rare back edge copies.  `undo` goes through an empty asm so that the
   // compiler cannot peel the loop back into the two copies.
+  auto step_pf = [&](const int4 e, const uint32_t word, const int thr_u, const uint32_t slot) -> bool {
+    const uint32_t msk = (uint32_t)e.y;
+    const uint32_t waddr = tu_my + (uint32_t)e.x;
+    const bool up = (word & msk) != 0u;
+    uint32_t rp = slot + (up ? (uint32_t)(ROW * 4) : 0u);
+    const int thr = thr_u - (up ? -e.z : e.z);
+    int undo = 0;
+    bool ok = false;
+    for (;;) {
+      const float acc = multiply(rp, true);
+      asm volatile("" : "+r"(undo));
+      if (undo) break;
+      int v = __float2int_rn(fmaf(acc, LEAN_FX, nlg)) >> 6;
+      if (hl == 0) v -= thr;
+      const int s_lo = __reduce_add_sync(0xffffffffu, v & ~m_hi);
+      const int s_hi = __reduce_add_sync(0xffffffffu, v & m_hi);
+      if (__builtin_expect(((s_lo & ~m_hi) | (s_hi & m_hi)) > 0, 1)) {
+        nlg = fmaf(acc, -LEAN_FX, 32.0f);
+        ++n_acc;
+        hw_sts32(waddr, word ^ msk);
+        ok = true;
+        break;
+      }
+      rp = 2u * slot + (uint32_t)(ROW * 4) - rp;
+      undo = 1;
+    }
+    return ok;
+  };
   auto step = [&](const int4 e, const uint32_t slot, const int tb) {
     const uint32_t msk = (uint32_t)e.y;
     const uint32_t waddr = tu_my + (uint32_t)e.x;
@@ -366,8 +398,30 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
     const uint32_t tbase = tab_addr + (buf << LEAN_TSH) * 16u;
     const bool whole = pos >= 0 && pos + T <= (int)n_steps && left >= T;
     if (whole) {
+      if constexpr (PF) {
+        int4 e = hw_lds128i(tbase);
+        uint32_t word = hw_lds32(tu_my + (uint32_t)e.x);
+        int thr_u = (int)hw_lds32(tu_my + 4u * (uint32_t)tb0);
 #pragma unroll UNR
-      for (int tt = 0; tt < T; ++tt) step(hw_lds128i(tbase + 16u * tt), cbase + (uint32_t)tt * (uint32_t)(2 * ROW * 4), tb0 + tt);
+        for (int tt = 0; tt < T; ++tt) {
+          int4 en = e;
+          uint32_t wn = word;
+          int tn = thr_u;
+          if (tt + 1 < T) {
+            en = hw_lds128i(tbase + 16u * (tt + 1));
+            wn = hw_lds32(tu_my + (uint32_t)en.x);
+            tn = (int)hw_lds32(tu_my + 4u * (uint32_t)(tb0 + tt + 1));
+          }
+          const bool ok = step_pf(e, word, thr_u, cbase + (uint32_t)tt * (uint32_t)(2 * ROW * 4));
+          if (tt + 1 < T && ok && en.x == e.x) wn ^= (uint32_t)e.y;  // the word was read before this step's flip
+          e = en;
+          word = wn;
+          thr_u = tn;
+        }
+      } else {
+#pragma unroll UNR
+        for (int tt = 0; tt < T; ++tt) step(hw_lds128i(tbase + 16u * tt), cbase + (uint32_t)tt * (uint32_t)(2 * ROW * 4), tb0 + tt);
+      }
       s += T;
       left -= T;
     } else {
@@ -415,15 +469,15 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   if (a.n_accepted && hl == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-template <int NP, int GL, int UNR = 4, int W_ = 16, int SG = 2, int WA = W_>
+template <int NP, int GL, int UNR = 4, int W_ = 16, int SG = 2, int WA = W_, int PF = 0>
 static int launch_ratio_lean_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws16,
                                 const int *site_seq, const float *a0_seq, cudaStream_t st) {
   const size_t smem = lean_hw_smem_bytes(NP, W_, (net->n_visible + 31) >> 5);
-  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA>,
+  cudaError_t rc = cudaFuncSetAttribute(sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA, PF>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (rc != cudaSuccess) NKFB_FAIL(h, NKFB_ERR_UNSUPPORTED, "sampler needs %zu B of shared memory", smem);
   const int64_t blocks = (a.n_chains + (int64_t)2 * WA - 1) / ((int64_t)2 * WA);
-  sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA><<<(unsigned)blocks, W_ * 32, smem, st>>>(
+  sample_ratio_lean_hw_kernel<NP, GL, UNR, W_, SG, WA, PF><<<(unsigned)blocks, W_ * 32, smem, st>>>(
       make_netdev<float>(net), (const float *)ws16, (float)a.s0, (float)a.s1, a, site_seq, a0_seq);
   NKFB_LAUNCHED(h);
   return NKFB_OK;

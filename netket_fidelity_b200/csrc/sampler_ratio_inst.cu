@@ -118,7 +118,7 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
         if (lean && a.ws_hw != nullptr) {
           // 14-warp CTAs for launches below one wave (tuning builds only: measured slower, sampler_hw_inst.cu)
           int warps = 16;
-          if (getenv("NKFB_HW_W14") && head == a.n_chains && blocks < slots && (head + 27) / 28 <= slots)
+          if (getenv("NKFB_HW_W14") && head == a.n_chains && blocks < slots)
             warps = atoi(getenv("NKFB_HW_W14"));
           rc = dispatch_ratio_hw_f32(h, net, ah, a.np_hw, gl_one, warps, st);
         }
