@@ -131,12 +131,11 @@ class InfidelityStep:
         if cfg.one_collective:
             return 1
         if K is None:
-            # automatic: single precision, the shape range of the CTA-synchronous samplers (32 chains per CTA), both
-            # launches together leave >= 16 SMs idle, segments large enough for the tensor-core estimator
-            sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
-            ctas = 2 * ((self.local_chains + 31) // 32)
+            # automatic: single precision, the shape range of the CTA-synchronous samplers (32 chains per CTA), the LAST
+            # wave of the two launches' CTAs leaves >= 16 SMs idle (at most two waves: beyond that the dispatcher mixes
+            # kernels), segments large enough for the tensor-core estimator
             ok = (self.cdtype == torch.complex64 and 161 <= self.M <= 512 and self.N <= 128 and cfg.site_mode == 0
-                  and self.local_chains >= 1024 and ctas <= sm - 16 and cfg.chain_length % 2 == 0
+                  and self.local_chains >= 1024 and self._idle_sms() >= 16 and cfg.chain_length % 2 == 0
                   and self.S_local // 2 >= 2048)
             # two segments: every further one costs ~0.1 ms of pipeline start-up and straggler wait per sampler launch
             # (measured on the 8-GPU shard of C4: K = 1 / 2 / 4 / 8 -> 6.40 / 6.29 / 6.41 / 6.75 ms per step)
@@ -145,6 +144,14 @@ class InfidelityStep:
         if K > 1 and cfg.chain_length % K != 0:
             raise ValueError(f"stream_segments = {K} does not divide chain_length = {cfg.chain_length}")
         return K
+
+    def _idle_sms(self):
+        """SMs without a sampler CTA during the last wave of the two sampler launches of this rank (one 16-warp CTA of
+        32 chains per SM); 0 when the launches need more than two waves."""
+        sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        ctas = 2 * ((self.local_chains + 31) // 32)
+        waves = (ctas + sm - 1) // sm
+        return waves * sm - ctas if waves <= 2 else 0
 
     def _sample_streamed(self, psi: nv.RbmSpec, phi: nv.RbmSpec):
         """K segments of chain_length / K samples per chain; the two families of a segment on two high-priority streams,
@@ -163,8 +170,7 @@ class InfidelityStep:
         self.acc.zero_()
         for st in (self.psi_stream, self.side_stream, self.est_stream):
             st.wait_stream(main)
-        sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
-        idle = max(1, sm - 2 * ((self.local_chains + 31) // 32))
+        idle = max(1, self._idle_sms())
         self.h.set_sampler_share(2)
         try:
             for k in range(K):

@@ -55,10 +55,11 @@ def test_streamed_step_is_the_unstreamed_step_float64():
             assert np.max(np.abs(a[1] - b[1])) <= 1e-12 * max(1.0, np.max(np.abs(a[1])))
 
 
-def test_streamed_step_on_the_eight_gpu_shard_of_c4():
-    """complex64, N = 100, M = 400, 2048 chains x 64 (one rank of an 8-GPU C4 job): the engine picks K = 2 by itself
-    (both sampler launches leave 20 SMs idle); tensor-core pass A per segment with the CTA limit, half-warp sampler with
-    reused tables.  Against the unstreamed step from the same seed: the acceptance decisions differ only by single-precision
+@pytest.mark.parametrize("n_chains", [2048, 4096])
+def test_streamed_step_on_the_multi_gpu_shards_of_c4(n_chains):
+    """complex64, N = 100, M = 400, 2048 / 4096 chains x 64 (one rank of an 8- / 4-GPU C4 job): the engine picks K = 2 by
+    itself (the last wave of the two sampler launches leaves 20 / 40 SMs idle); tensor-core pass A per segment with the CTA
+    limit, half-warp sampler with reused tables.  Against the unstreamed step from the same seed: the acceptance decisions differ only by single-precision
     rounding (z is refreshed at the start of every call), so nearly all chains emit identical samples, and F and the
     gradient agree within the Monte-Carlo error of the few chains that differ."""
     w = make_workload("C4")
@@ -67,7 +68,7 @@ def test_streamed_step_on_the_eight_gpu_shard_of_c4():
     psi, phi = _specs(N, M, torch.complex64, w["vb"], 0.01)
     out = {}
     for K in (None, 1):
-        cfg = StepConfig(2048, 64, 5, N, seed=20261019, cv_coeff=-0.5, stream_segments=K)
+        cfg = StepConfig(n_chains, 64, 5, N, seed=20261019, cv_coeff=-0.5, stream_segments=K)
         eng = InfidelityStep(N, M, cfg, w["mode"], U, Ud, device=torch.device(DEV))
         assert eng.K == (2 if K is None else 1)
         eng.step(psi, phi)
@@ -76,7 +77,7 @@ def test_streamed_step_on_the_eight_gpu_shard_of_c4():
         sig, eta = _chain_major(eng)
         out[K] = (sums.cpu().numpy().copy(), grad.cpu().numpy().copy(), sig.cpu(), eta.cpu(), eng.n_accepted.cpu().numpy().copy())
     a, b = out[None], out[1]
-    assert a[0][4] == b[0][4] == 2048 * 64
+    assert a[0][4] == b[0][4] == n_chains * 64
     same = ((a[2] == b[2]).flatten(1).all(dim=1) & (a[3] == b[3]).flatten(1).all(dim=1)).float().mean().item()
     assert same > 0.9, same
     Fa, Fb = a[0][0] / a[0][4], b[0][0] / b[0][4]
