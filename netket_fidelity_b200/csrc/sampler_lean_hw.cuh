@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32 * W_, 1) sample_ratio_lean_hw_kernel(NetDev
   if (a.n_accepted && hl == 0 && n_acc) atomicAdd(a.n_accepted, (unsigned long long)n_acc);
 }
 
-template <int NP, int GL, int UNR = 4, int W_ = 16, int SG = 2, int WA = W_, int PF = 0>
+template <int NP, int GL, int UNR = 8, int W_ = 16, int SG = 2, int WA = W_, int PF = 0>
 static int launch_ratio_lean_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, const void *ws16,
                                 const int *site_seq, const float *a0_seq, cudaStream_t st) {
   const size_t smem = lean_hw_smem_bytes(NP, W_, (net->n_visible + 31) >> 5);

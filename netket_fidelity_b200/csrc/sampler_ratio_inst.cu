@@ -79,8 +79,8 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
     } else if (cta_ok && CC == 2 && sizeof(NKFB_RT) == 4) {
       // one wave of the CTA-synchronous kernel in rounds of the pipelined one (3.92 ms per round at the C4 shape): 1.70 for
       // the round-1 kernel (6.65 ms per wave), 1.39 for the lean kernel with TMA row staging (5.46 ms)
-      // 1.32 for the half-warp lean kernel (5.16 ms)
-      const double wave = getenv("NKFB_NOLEAN") ? 1.70 : (a.ws_hw != nullptr ? 1.32 : 1.39);
+      // 1.25 for the half-warp lean kernel (4.88 ms)
+      const double wave = getenv("NKFB_NOLEAN") ? 1.70 : (a.ws_hw != nullptr ? 1.25 : 1.39);
       double best = (double)((blocks + slots - 1) / slots) * wave;  // CTA-synchronous kernel alone
       int64_t best_head = a.n_chains;
       for (int64_t k = full_waves; k >= 0; --k) {
