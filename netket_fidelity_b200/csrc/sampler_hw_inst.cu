@@ -36,8 +36,8 @@ static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int 
 #ifdef NKFB_TUNE
   if (warps == 114) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 14>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   if (warps == 112) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 12>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-  if (warps == 204) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 4, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
-  if (warps == 216) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 16, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  if (warps == 204) return launch_ratio_lean_hw<NP, 4, 8, 16, 1, 16, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  if (warps == 216) return launch_ratio_lean_hw<NP, 4, 8, 16, 2, 16, 1>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   if (warps == 108) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   if (warps == 104) return launch_ratio_lean_hw<NP, 4, 4, 16, 2, 4>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   if (warps == 14) {
