@@ -382,7 +382,7 @@ def hw_kernel(monkeypatch):
 
 
 @pytest.mark.parametrize("N,M,B", [(100, 400, 0.0), (100, 400, 5.0), (64, 330, 0.0), (37, 384, 0.0), (100, 448, 0.0),
-                                   (128, 470, 0.0), (40, 512, 0.0), (40, 512, 5.0)])
+                                   (128, 470, 0.0), (40, 512, 0.0), (40, 512, 5.0), (150, 400, 0.0), (7, 416, 0.0)])
 def test_half_warp_kernel_agrees_with_the_32_lane_lean_kernel(h, algo, hw_kernel, N, M, B):
     """sampler_lean_hw.cuh (a chain on 16 lanes, both chains of a warp in one instruction stream) against the 32-lane
     lean kernel on every instantiated width (11..16 pairs per lane), both range windows (B = 5: one logarithm per
