@@ -45,6 +45,13 @@ static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int 
     return launch_ratio_lean_hw<NP, 4, 4, 14>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   }
 #endif
+  // tail of a large launch (the chains beyond its last full wave): 16-warp CTAs of which 8 warps carry chains -- 16 chains per
+  // CTA, two warps per scheduler: a step lasts 0.69 of a full CTA's (3.54 against 5.12 ms per wave before the full unroll),
+  // shorter than a round of the one-chain-per-warp kernel (3.92 ms)
+  if (warps == 8) {
+    if (gl_one) return launch_ratio_lean_hw<NP, 1, 8, 16, 2, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+    return launch_ratio_lean_hw<NP, 4, 8, 16, 2, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
+  }
   // the 8 steps of a chunk fully unrolled (UNR = 8): 4.88 ms per wave against 5.13 (UNR = 4), 5.33 (2), 5.07 (1) at C4
   if (gl_one) return launch_ratio_lean_hw<NP, 1, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   return launch_ratio_lean_hw<NP, 4, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);

@@ -83,10 +83,14 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
       const double wave = getenv("NKFB_NOLEAN") ? 1.70 : (a.ws_hw != nullptr ? 1.25 : 1.39);
       double best = (double)((blocks + slots - 1) / slots) * wave;  // CTA-synchronous kernel alone
       int64_t best_head = a.n_chains;
+      // the rest: half-warp kernel with 8 of 16 warps carrying chains (16 chains per CTA, 0.87 of a pipelined round) when it
+      // fits one wave of those, else rounds of the pipelined kernel
+      const bool tail8 = a.ws_hw != nullptr && !getenv("NKFB_HW_NOTAIL8");
       for (int64_t k = full_waves; k >= 0; --k) {
         const int64_t hd = std::min<int64_t>(a.n_chains, k * slots * per_cta);
         const int64_t rest = a.n_chains - hd;
-        const double t = (double)k * wave + (rest > 0 ? std::max(1.0, (double)rest / round_chains) : 0.0);
+        const double t_rest = rest <= 0 ? 0.0 : ((tail8 && rest <= 16 * slots) ? 0.87 : std::max(1.0, (double)rest / round_chains));
+        const double t = (double)k * wave + t_rest;
         if (t < best * 0.98) {
           best = t;
           best_head = hd;
@@ -139,10 +143,21 @@ static int go(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int gl_
       at.chain_offset = a.chain_offset + (uint64_t)head;
       at.chain_state = a.chain_state + head * W32;
       at.samples = a.samples ? a.samples + head * a.chain_length * W32 : nullptr;
+      if constexpr (sizeof(NKFB_RT) == 4 && CC == 2) {
+        if (lean && a.ws_hw != nullptr && at.n_chains <= 16 * slots && !getenv("NKFB_HW_NOTAIL8"))
+          return dispatch_ratio_hw_f32(h, net, at, a.np_hw, gl_one, 8, st);
+      }
       constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
       if (gl_one) return launch_ratio_pipe<NKFB_RT, NP, 1, PMB>(h, net, at, ws, st);
       return launch_ratio_pipe<NKFB_RT, NP, GW, PMB>(h, net, at, ws, st);
     }
+  }
+  if constexpr (sizeof(NKFB_RT) == 4 && NP >= 6 && NP <= 8) {
+    // a whole launch of at most 16 chains per SM: the 8-of-16-warps form of the half-warp kernel (see the tail above)
+    int share = h->opt_sampler_share > 0 ? h->opt_sampler_share : 1;
+    if (a.ws_hw != nullptr && a.site_seq != nullptr && a.n_chains <= (int64_t)16 * std::max(1, h->sm_count / share) &&
+        !getenv("NKFB_HW_NOTAIL8") && !getenv("NKFB_NOLEAN") && !getenv("NKFB_RATIO_NOCTA"))
+      return dispatch_ratio_hw_f32(h, net, a, a.np_hw, gl_one, 8, st);
   }
   if (net->n_visible <= 32 * PIPE_WR && !getenv("NKFB_RATIO_NOPIPE")) {
     constexpr int PMB = PipeShape<NKFB_RT, NP>::MB;
