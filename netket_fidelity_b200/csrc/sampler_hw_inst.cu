@@ -52,6 +52,8 @@ static int go_hw(nkfb_handle_t h, const nkfb_rbm_t *net, const SampArgs &a, int 
     if (gl_one) return launch_ratio_lean_hw<NP, 1, 8, 16, 2, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
     return launch_ratio_lean_hw<NP, 4, 8, 16, 2, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   }
+  // (12 warps carrying chains -- 24 chains per CTA -- for a rest that does not fit 16 per CTA was measured too: the simulated
+  // 4-GPU shard went from 11.62 to 12.74 ms; a wave of such CTAs lasts 4.87 ms with 43 of them but 5.38 ms with 86)
   // the 8 steps of a chunk fully unrolled (UNR = 8): 4.88 ms per wave against 5.13 (UNR = 4), 5.33 (2), 5.07 (1) at C4
   if (gl_one) return launch_ratio_lean_hw<NP, 1, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
   return launch_ratio_lean_hw<NP, 4, 8>(h, net, a, a.ws_hw, a.site_seq, (const float *)a.a0_seq, st);
