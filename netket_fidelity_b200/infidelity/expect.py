@@ -23,6 +23,37 @@ def _allreduce(t):
 
 
 _side_streams = {}
+_stream_sets = {}
+
+
+def _streamed_streams(dev):
+    """(psi sampler, phi sampler, estimator) streams of the streamed path: the samplers above the estimator in priority, so
+    that the estimator's CTAs only take the SMs the sampler launches leave idle."""
+    key = dev.index
+    if key not in _stream_sets:
+        _stream_sets[key] = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=-1),
+                             torch.cuda.Stream(device=dev, priority=0))
+    return _stream_sets[key]
+
+
+def _streamed_idle_sms(vstate, target):
+    """SMs without a sampler CTA during the last wave of the two sampler launches, when pass A can be streamed under the
+    sampling (same rule as engine.InfidelityStep._pick_segments); 0 otherwise."""
+    import os
+    if os.environ.get("NKFB_STREAM_SEGMENTS", "") == "1":
+        return 0
+    n = vstate._n_chains_local
+    cl = vstate._chain_length
+    if (vstate._cdtype != torch.complex64 or target._cdtype != torch.complex64 or not (161 <= vstate._M <= 512)
+            or target._M != vstate._M or vstate._N > 128 or vstate.sampler.site_mode != "shared"
+            or target.sampler.site_mode != "shared" or target._op_spec() is not None or vstate._op_spec() is not None
+            or n < 1024 or target._n_chains_local != n or target._chain_length != cl or cl % 2 or n * (cl // 2) < 2048):
+        return 0
+    sm = torch.cuda.get_device_properties(vstate.device).multi_processor_count
+    ctas = 2 * ((n + 31) // 32)
+    waves = (ctas + sm - 1) // sm
+    idle = waves * sm - ctas if waves <= 2 else 0
+    return idle if idle >= 16 else 0
 
 
 def _side_stream(dev):
@@ -54,43 +85,96 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
         op1, op2, op4 = op._U._spec(dev), op._U_dagger._spec(dev), None
     if vstate._spec().code != target._spec().code:
         raise TypeError("the variational state and the target must share a parameter precision")
-    if vstate._samples_packed is None and target._samples_packed is None and target is not vstate:
-        # both chain families need fresh samples (the driver's reset(), driver/infidelity_optimizer.py:142-143):
-        # run the two sampler launches on two streams so that the tail of one overlaps the other
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
-        side.wait_stream(main)
-        vstate._h.set_sampler_share(2)      # two launches of equal size side by side (include/nkfb200.h)
-        try:
-            vstate.sample()
-            with torch.cuda.stream(side):
-                target.sample()
-        finally:
-            vstate._h.set_sampler_share(1)
-        main.wait_stream(side)
-    sigma = vstate.samples_packed()
-    eta = target.samples_packed()
-    if sigma.shape != eta.shape:
-        raise ValueError(f"both states need the same number of samples per rank, got {tuple(sigma.shape[:2])} "
-                         f"and {tuple(eta.shape[:2])}")
     h = vstate._h
-    W32 = sigma.shape[-1]
     psi, phi = vstate._spec(), target._spec()
     ls = vstate._ls
-    acc = torch.zeros((8 + 2 * vstate._flat.numel(),), dtype=torch.float64, device=dev)
-    sums, gacc = acc[:8], acc[8:]
-    log_val, L, rho1, _ = h.infidelity_fwd(psi, phi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff,
-                                           op1, op2, op4, sums=sums)
+    fresh = vstate._samples_packed is None and target._samples_packed is None and target is not vstate
+    idle = _streamed_idle_sms(vstate, target) if fresh else 0
+    if idle:
+        # A shard whose sampler launches leave SMs idle (one rank of a 4- / 8-GPU C4 job): sample in two segments and run
+        # pass A of the first on the idle SMs while the second is being sampled (engine.py).  Pass A /
+        # pass B work on segment-major lists ([segment][chain][sample]); the samples the states keep and the local
+        # estimators handed to the chain statistics are put back into NetKet's (chain, sample) order.
+        K = 2
+        n, cl, W32 = vstate._n_chains_local, vstate._chain_length, vstate._W32
+        seg = cl // K
+        S_seg = n * seg
+        main = torch.cuda.current_stream(dev)
+        s_psi, s_phi, s_est = _streamed_streams(dev)
+        h.set_sampler_share(2)
+        try:
+            for k in range(K):
+                nd_psi = vstate.n_discard_per_chain if k == 0 else 0
+                nd_phi = target.n_discard_per_chain if k == 0 else 0
+                if k == 0:
+                    # the first sampler launches go out before anything else is allocated: the GPU is idle until they start
+                    s_psi.wait_stream(main)
+                    sig_seg = torch.empty((K, n, seg, W32), dtype=torch.int32, device=dev)
+                with torch.cuda.stream(s_psi):
+                    vstate._sample_segment(seg, nd_psi, sig_seg[k], tables_valid=k > 0)
+                if k == 0:
+                    s_phi.wait_stream(main)
+                    eta_seg = torch.empty_like(sig_seg)
+                with torch.cuda.stream(s_phi):
+                    target._sample_segment(seg, nd_phi, eta_seg[k], tables_valid=k > 0)
+                if k == 0:
+                    acc = torch.zeros((8 + 2 * vstate._flat.numel(),), dtype=torch.float64, device=dev)
+                    sums, gacc = acc[:8], acc[8:]
+                    log_val = torch.empty((K * S_seg,), dtype=vstate._cdtype, device=dev)
+                    rho1 = torch.empty_like(log_val)
+                    L_seg = torch.empty((K * S_seg,), dtype=torch.float32, device=dev)
+                    s_est.wait_stream(main)
+                s_est.wait_stream(s_psi)
+                s_est.wait_stream(s_phi)
+                with torch.cuda.stream(s_est):
+                    h.set_fwd_max_ctas(2 * idle if k < K - 1 else 0)
+                    sl = slice(k * S_seg, (k + 1) * S_seg)
+                    h.infidelity_fwd(psi, phi, sig_seg[k].view(-1, W32), eta_seg[k].view(-1, W32), ls, op.cv_coeff, op1, op2,
+                                     op4, sums=sums, out=(log_val[sl], L_seg[sl], rho1[sl]))
+        finally:
+            h.set_sampler_share(1)
+            h.set_fwd_max_ctas(0)
+        main.wait_stream(s_est)       # s_est waited for both sampler streams: everything above is ordered before `main` now
+        sigma, eta = sig_seg.view(-1, W32), eta_seg.view(-1, W32)          # segment-major, as log_val / rho1 are
+        vstate._samples_packed = sig_seg.permute(1, 0, 2, 3).reshape(n, cl, W32)
+        target._samples_packed = eta_seg.permute(1, 0, 2, 3).reshape(n, cl, W32)
+        L = L_seg.view(K, n, seg).permute(1, 0, 2).reshape(-1)              # (chain, sample) order for the statistics
+        chain_len = cl
+    else:
+        if fresh:
+            # both chain families need fresh samples (the driver's reset(), driver/infidelity_optimizer.py:142-143):
+            # run the two sampler launches on two streams so that the tail of one overlaps the other
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            vstate._h.set_sampler_share(2)      # two launches of equal size side by side (include/nkfb200.h)
+            try:
+                vstate.sample()
+                with torch.cuda.stream(side):
+                    target.sample()
+            finally:
+                vstate._h.set_sampler_share(1)
+            main.wait_stream(side)
+        acc = torch.zeros((8 + 2 * vstate._flat.numel(),), dtype=torch.float64, device=dev)
+        sums, gacc = acc[:8], acc[8:]
+        sigma = vstate.samples_packed()
+        eta = target.samples_packed()
+        if sigma.shape != eta.shape:
+            raise ValueError(f"both states need the same number of samples per rank, got {tuple(sigma.shape[:2])} "
+                             f"and {tuple(eta.shape[:2])}")
+        W32 = sigma.shape[-1]
+        chain_len = eta.shape[-2]
+        sigma, eta = sigma.view(-1, W32), eta.view(-1, W32)
+        log_val, L, rho1, _ = h.infidelity_fwd(psi, phi, sigma, eta, ls, op.cv_coeff, op1, op2, op4, sums=sums)
     _allreduce(sums)
     # n_chains = sigma_t.shape[-2] (overlap/expect.py:72): the reference hands the CHAIN LENGTH to
     # nkjax.expect as "n_chains"; mean, variance and gradient do not depend on it
     # the statistics kernels go into the stream here; their read-back (a host synchronisation) waits until the
     # gradient has been enqueued behind them, so that the GPU does not idle while the host does the statistics
-    stats_ctx = vstate._stats_begin(L, eta.shape[-2], sums=sums)
+    stats_ctx = vstate._stats_begin(L, chain_len, sums=sums)
     flat = None
     if return_grad:
-        h.infidelity_grad(psi, sigma.view(-1, W32), eta.view(-1, W32), ls, op.cv_coeff, log_val, rho1, sums,
-                          op2=op2, grad_acc=gacc)
+        h.infidelity_grad(psi, sigma, eta, ls, op.cv_coeff, log_val, rho1, sums, op2=op2, grad_acc=gacc)
         _allreduce(gacc)
         flat = h.grad_finalize(gacc, sums, vstate._flat.numel(), vstate._cdtype)
     F_stats = vstate._stats_end(stats_ctx, L)

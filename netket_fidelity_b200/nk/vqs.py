@@ -270,6 +270,22 @@ class MCState(_RBMStateBase):
         self._samples_packed = out
         return out
 
+    def _sample_segment(self, seg_len, n_discard, out, tables_valid):
+        """One segment of a sampling pass split over several nkfb_sample calls (infidelity/expect.py, streamed pass A): the
+        chains continue from their device-resident configurations exactly as from one `sample()` to the next; `out`
+        (n_chains_local, seg_len, W32) receives the segment.  The caller assembles `_samples_packed`."""
+        net = self._spec()
+        if self._ws is None:
+            self._ws = self._h.sample_workspace(net)
+        self._h.sample(net, self._chain_state, seg_len, n_discard, self.sampler.sweep_size, self._sampler_seed, self._ls,
+                       op=self._op_spec(), chain_offset=self._rank * self._n_chains_local, step_offset=self._steps_done,
+                       site_mode=0 if self.sampler.site_mode == "shared" else 1,
+                       init_random=not self._chains_initialised, n_accepted=self._n_accepted, workspace=self._ws, out=out,
+                       tables_valid=tables_valid)
+        self._chains_initialised = True
+        self._steps_done += (seg_len + n_discard) * self.sampler.sweep_size
+        self._n_steps_total += (seg_len + n_discard) * self.sampler.sweep_size * self._n_chains_local
+
     def samples_packed(self):
         """(n_chains_local, chain_length, W32) int32: bit-packed samples, sampled lazily."""
         if self._samples_packed is None:

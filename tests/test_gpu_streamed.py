@@ -85,3 +85,52 @@ def test_streamed_step_on_the_multi_gpu_shards_of_c4(n_chains):
     assert abs(Fa - Fb) < 5 * np.sqrt(8.0 * max(var, 1e-12) / b[0][4]) * np.sqrt(1.0 - same + 1e-3) + 1e-6, (Fa, Fb)
     assert np.max(np.abs(a[1] - b[1])) < 0.1 * np.max(np.abs(b[1])), np.max(np.abs(a[1] - b[1])) / np.max(np.abs(b[1]))
     assert abs(int(a[4].sum()) - int(b[4].sum())) < 1e-3 * b[4].sum()
+
+
+def test_public_path_streams_pass_a_on_a_shard(monkeypatch):
+    """`MCState.expect_and_grad(InfidelityOperator)` on the 8-GPU shard shape of C4 (2048 chains x 64 per family): the
+    public path samples in two segments and runs pass A of the first under the second (infidelity/expect.py), exactly
+    when the engine does.  Against the same call with NKFB_STREAM_SEGMENTS=1 (one sampling pass, one pass A): the states
+    keep their samples in NetKet's (chain, sample) layout, nearly all chains emit identical samples, mean / variance /
+    gradient agree within the Monte-Carlo error of the few that differ, and the chain statistics (error_of_mean,
+    tau_corr, R_hat: functions of the per-chain order of the local estimators) agree."""
+    import netket_fidelity_b200 as nkf
+    from netket_fidelity_b200 import nk
+    from netket_fidelity_b200.infidelity import expect as ex
+    w = make_workload("C4")
+    N, M = w["N"], w["M"]
+    dev = torch.device(DEV)
+    hi = nk.hilbert.Spin(0.5, N)
+    out = {}
+    for mode in ("streamed", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("NKFB_STREAM_SEGMENTS", "1")
+        else:
+            monkeypatch.delenv("NKFB_STREAM_SEGMENTS", raising=False)
+        sa = nk.sampler.MetropolisLocal(hi, n_chains=2048, sweep_size=N)
+        ma = nk.models.RBM(alpha=M // N, param_dtype="complex64", use_visible_bias=w["vb"])
+        mk = lambda seed: {"params": (lambda t: {"Dense": {"kernel": t[0].to(dev), "bias": t[1].to(dev)},
+                                                **({"visible_bias": t[2].to(dev)} if t[2] is not None else {})})(
+            random_rbm(N, M, seed, torch.complex64, w["vb"]))}
+        psi = nk.vqs.MCState(sa, ma, n_samples=2048 * 64, n_discard_per_chain=5, seed=1, device=dev, variables=mk(1234))
+        phi = nk.vqs.MCState(sa, ma, n_samples=2048 * 64, n_discard_per_chain=5, seed=2, device=dev, variables=mk(5678))
+        assert (ex._streamed_idle_sms(psi, phi) > 0) == (mode == "streamed")
+        U, Ud = nkf.operator.Rx(hi, 0, 0.1), nkf.operator.Rx(hi, 0, -0.1)
+        op = nkf.InfidelityOperator(phi, U=U, U_dagger=Ud, cv_coeff=-0.5, is_unitary=True)
+        psi.expect_and_grad(op)                      # first step: random initial configurations
+        psi.reset(); phi.reset()
+        st, grad = psi.expect_and_grad(op)
+        torch.cuda.synchronize()
+        sig, eta = psi.samples_packed(), phi.samples_packed()
+        assert tuple(sig.shape) == (2048, 64, (N + 31) // 32) and tuple(eta.shape) == tuple(sig.shape)
+        out[mode] = (st, psi._last_flat_grad.cpu().numpy().copy(), sig.cpu(), eta.cpu(), psi.acceptance)
+    a, b = out["streamed"], out["plain"]
+    same = ((a[2] == b[2]).flatten(1).all(dim=1) & (a[3] == b[3]).flatten(1).all(dim=1)).float().mean().item()
+    assert same > 0.9, same
+    sa_, sb_ = a[0], b[0]
+    assert abs(sa_.mean - sb_.mean) < 5 * float(sb_.error_of_mean) * np.sqrt(1.0 - same + 1e-3) + 1e-6
+    assert abs(sa_.variance - sb_.variance) < 0.05 * sb_.variance + 1e-9
+    assert abs(float(sa_.error_of_mean) - float(sb_.error_of_mean)) < 0.1 * float(sb_.error_of_mean)
+    assert abs(float(sa_.R_hat) - float(sb_.R_hat)) < 0.01 and abs(float(sa_.tau_corr) - float(sb_.tau_corr)) < 0.1 + 0.1 * abs(float(sb_.tau_corr))
+    assert np.max(np.abs(a[1] - b[1])) < 0.1 * np.max(np.abs(b[1]))
+    assert abs(a[4] - b[4]) < 1e-3
