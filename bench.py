@@ -182,7 +182,9 @@ def bench_config(name, w, n_gpus, site_mode=0):
             "global_sample_pairs": w["n_chains"] * w["chain_length"], "n_chains_per_family": w["n_chains"],
             "chain_length": w["chain_length"], "site_mode": site_mode,
             "parallelism": f"chains sharded over {n_gpus} GPU(s)",
-            "l2": "160 MiB scratch buffer (larger than the 126 MB L2) rewritten between timed steps (L2 flush, inside the timed region)"}
+            "l2": "160 MiB scratch buffer (larger than the 126 MB L2) rewritten between the timed steps (L2 flush); the flushes "
+                  "are timed by their own CUDA events and subtracted from the bracket of the K steps (ms_per_step_bracket "
+                  "and l2_flush_ms in the line give the raw bracket and the flush)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -217,6 +219,16 @@ class Ctx:
         return float(t.item())
 
 
+def net_of_flushes(ctx, e0, e1, flush_pairs):
+    """(ms_total, ms_bracket, flush_ms): the bracket e0 -> e1 of K steps minus the K L2 flushes between them (K x the
+    median of their event-timed intervals: a flush is one fill kernel, the median keeps a host hiccup between the two
+    records out of the subtraction), max over the ranks of both."""
+    bracket = e0.elapsed_time(e1)
+    iv = sorted(a.elapsed_time(b) for a, b in flush_pairs)
+    flush = iv[len(iv) // 2] if iv else 0.0
+    return ctx.max_over_ranks(bracket - flush * len(iv)), ctx.max_over_ranks(bracket), flush
+
+
 def make_engine(ctx, name, dtype, site_mode, one_collective=False):
     from netket_fidelity_b200 import _native as nv
     from netket_fidelity_b200.engine import InfidelityStep, StepConfig
@@ -236,29 +248,36 @@ def make_engine(ctx, name, dtype, site_mode, one_collective=False):
 
 
 def time_engine(ctx, eng, specs, steps, warmup):
-    """W untimed + K timed steps of the device-resident engine: barrier + synchronize on both sides, CUDA events on the
-    launching stream, the L2 flush inside the timed region, max over ranks."""
+    """W untimed + K timed steps of the device-resident engine, bracketed by a barrier + synchronize and one pair of CUDA
+    events (on the launching stream) on both sides.  The L2 is flushed BETWEEN the timed steps (a 160 MiB buffer rewritten
+    on the same stream); each flush is timed by its own pair of events and the K flush intervals are subtracted from the
+    bracket: `ms_total` = max over the ranks of (bracket - flushes) -- the K steps and every gap between them, not the
+    flushes, which are the measurement's and not the workload's; `ms_bracket` (max over the ranks of the raw bracket) and
+    `flush_ms` are reported beside it."""
     for _ in range(warmup):
         ctx.flush.zero_()
         eng.step(specs["psi"], specs["phi"])
     ctx.barrier()
     samp_ev = [(ctx.ev(), ctx.ev()) for _ in range(steps)]
     est_ev = [(ctx.ev(), ctx.ev(), ctx.ev()) for _ in range(steps)]
+    flush_ev = [ctx.ev() for _ in range(steps)]
     launches0 = eng.h.launches
     ctx.barrier()
     e0, e1 = ctx.ev(), ctx.ev()
     t_wall0 = time.time()
     e0.record()
     for i in range(steps):
+        flush_ev[i].record()
         ctx.flush.zero_()
-        samp_ev[i][0].record()
+        samp_ev[i][0].record()                      # start of step i: the flush before it has completed on this stream
         eng.sample(specs["psi"], specs["phi"])
         samp_ev[i][1].record()
         sums, L, grad = eng.estimate(specs["psi"], specs["phi"], events=est_ev[i])
     e1.record()
     ctx.barrier()
-    ms_total = ctx.max_over_ranks(e0.elapsed_time(e1))
-    return dict(ms_total=ms_total, ms_per_step=ms_total / steps, launches=eng.h.launches - launches0,
+    ms_total, ms_bracket, flush_ms = net_of_flushes(ctx, e0, e1, [(f, s[0]) for f, s in zip(flush_ev, samp_ev)])
+    return dict(ms_total=ms_total, ms_per_step=ms_total / steps, ms_bracket=ms_bracket, flush_ms=flush_ms,
+                launches=eng.h.launches - launches0,
                 samp_ms=sum(a.elapsed_time(b) for a, b in samp_ev) / steps,
                 fwd_ms=sum(a.elapsed_time(b) for a, b, c in est_ev) / steps,
                 grad_ms=sum(b.elapsed_time(c) for a, b, c in est_ev) / steps,   # incl. the scalar all-reduce when N > 1
@@ -322,15 +341,17 @@ def time_renyi(ctx, name, dtype, steps, warmup):
         step()
     ctx.barrier()
     evs = [(ctx.ev(), ctx.ev()) for _ in range(steps)]
+    flush_ev = [ctx.ev() for _ in range(steps)]
     launches0 = h.launches
     e0, e1 = ctx.ev(), ctx.ev()
     e0.record()
     for i in range(steps):
+        flush_ev[i].record()
         ctx.flush.zero_()
         sums = step(evs[i])
     e1.record()
     ctx.barrier()
-    ms_total = ctx.max_over_ranks(e0.elapsed_time(e1))
+    ms_total, _, _ = net_of_flushes(ctx, e0, e1, [(f, e[0]) for f, e in zip(flush_ev, evs)])
     s = sums.cpu().numpy()
     S2 = float(-np.log2(s[0] / s[3])) if s[0] > 0 else float("nan")
     return w, dict(ms_total=ms_total, ms_per_step=ms_total / steps, launches=h.launches - launches0,
@@ -396,13 +417,16 @@ def run_b200(args):
             eng.step(specs["psi"], specs["phi"])
         ctx.barrier()
         g0, g1 = ctx.ev(), ctx.ev()
+        gf = [(ctx.ev(), ctx.ev()) for _ in range(args.steps)]
         g0.record()
         for i in range(args.steps):
+            gf[i][0].record()
             ctx.flush.zero_()
+            gf[i][1].record()
             eng.step(specs["psi"], specs["phi"])
         g1.record()
         ctx.barrier()
-        graph_ms = ctx.max_over_ranks(g0.elapsed_time(g1)) / args.steps
+        graph_ms = net_of_flushes(ctx, g0, g1, gf)[0] / args.steps
     # clocks under load: samples that arrived during the timed region; when it is shorter than nvidia-smi's period
     # (multi-GPU runs: tens of ms) every rank keeps running the same step, untimed, until rank 0 has two samples
     t_wall1 = time.time()
@@ -466,7 +490,17 @@ def run_b200(args):
     ffma = max(h.microbench(3, 4096), 1.0)
     mufu = max(h.microbench(0, 2048), 1.0)
     dfma = max(h.microbench(6, 2048), 1.0)
-    f64_block, others, one_coll = None, {}, None
+    f64_block, others, one_coll, per_chain = None, {}, None, None
+    if not args.no_others and args.site_mode == 0:
+        # the same step with NetKet's per-chain proposal sites (MetropolisLocal: every chain draws its own site; the
+        # one-chain-per-warp kernel samples it), beside the shared-site-sequence headline
+        _, engp, _, _, specsp, _ = make_engine(ctx, args.workload, args.dtype, 1)
+        rp = time_engine(ctx, engp, specsp, max(3, min(5, args.steps)), 3)
+        sp = rp["sums"].cpu().numpy()
+        per_chain = {"site_mode": SITE_MODES[1], "ms_per_step": rp["ms_per_step"],
+                     "value": engp.S_total / (rp["ms_per_step"] * 1e-3), "unit": UNIT, "sampler_ms": rp["samp_ms"],
+                     "infidelity": float(1.0 - sp[0] / sp[4])}
+        del engp, specsp
     if not args.no_others and world > 1 and w["mode"] == "upsi":
         # the same step with ONE all-reduce (engine option one_collective): pass B centred with the previous
         # step's F plus sum_s conj O_k(sigma_s); reported beside the two-collective headline, not instead of it
@@ -536,7 +570,8 @@ def run_b200(args):
         ]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_step_bracket": r["ms_bracket"] / args.steps,
+            "l2_flush_ms": r["flush_ms"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": bench_config(args.workload, w, world, args.site_mode),
             "clocks": clk,
@@ -567,6 +602,7 @@ def run_b200(args):
                if graph_ms else {}),
             **({"f64": f64_block} if f64_block else {}),
             **({"one_collective": one_coll} if one_coll else {}),
+            **({"per_chain_sites": per_chain} if per_chain else {}),
             **({"other_workloads": others} if others else {}),
         }
         if world == 1 and not args.no_cpu_baseline:
