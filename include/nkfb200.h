@@ -122,7 +122,12 @@ int64_t nkfb_launch_count(nkfb_handle_t h);
  * whether the chains beyond the last full wave of CTAs are handed to the one-chain-per-warp kernel. */
 /* NKFB_OPT_FWD_MAX_CTAS (default 0 = no limit): upper bound on the CTAs of the next nkfb_infidelity_fwd launches.  Lets a
  * caller run pass A on the SMs a concurrent sub-wave sampler launch leaves idle (engine.py, streamed segments). */
-enum { NKFB_OPT_SAMPLER_ALGO = 1, NKFB_OPT_SAMPLER_SHARE = 2, NKFB_OPT_FWD_MAX_CTAS = 3 };
+/* NKFB_OPT_TC_TABLES_VALID (default 0): 1 = the parameter tables of the tensor-core estimator / gradient kernels (bf16
+ * splits of the RBM kernels, written by nkfb_tc_prepare or by the last nkfb_infidelity_fwd / nkfb_infidelity_grad launch
+ * into handle-owned scratch) still match the parameter buffers: launches on the SAME buffers and shapes skip their
+ * preparation kernels (the pass A launches of the sample segments of one step; pass B after an early nkfb_tc_prepare).
+ * The caller clears it (0) before the parameters change; other buffers or shapes are re-prepared whatever the flag says. */
+enum { NKFB_OPT_SAMPLER_ALGO = 1, NKFB_OPT_SAMPLER_SHARE = 2, NKFB_OPT_FWD_MAX_CTAS = 3, NKFB_OPT_TC_TABLES_VALID = 4 };
 /* nkfb_sample_cfg_t.flags.  NKFB_SAMPLE_TABLES_VALID: `workspace` (caller-provided) still holds the parameter tables an
  * earlier nkfb_sample call wrote for the SAME net, local_states and plain target; their preparation kernels are skipped
  * (a chain sampled in several consecutive calls between two parameter updates).  Ignored for composite targets. */
@@ -177,6 +182,15 @@ int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t
                         const uint32_t *sigma, const uint32_t *eta, int64_t S,
                         const double local_states[2], double cv_coeff, void *log_val,
                         void *L, void *rho1, double *sums, void *stream);
+
+/* Parameter tables of the tensor-core forms of nkfb_infidelity_fwd (psi and phi) and nkfb_infidelity_grad (psi), written
+ * ahead of time on `stream` -- e.g. under the sampler launches of a step, so that the three small preparation kernels leave
+ * the critical path (reference: the parameters are fixed for the whole of one expect_and_grad call,
+ * infidelity/overlap_U/expect.py:88-157).  Use with NKFB_OPT_TC_TABLES_VALID = 1; the later launches must be ordered after
+ * `stream`.  phi may be NULL (gradient tables only).  Does nothing for shapes / dtypes the tensor-core kernels do not
+ * cover. */
+int nkfb_tc_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const double local_states[2],
+                    void *stream);
 
 /* ---- infidelity gradient (pass B) --------------------------------------- */
 /* Replaces nkjax.expect's backward + nkjax.vjp(conjugate=True)

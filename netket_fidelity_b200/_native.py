@@ -23,12 +23,13 @@ SYMBOLS = [
     "nkfb_pack", "nkfb_unpack", "nkfb_conn", "nkfb_logpsi", "nkfb_sample", "nkfb_sample_workspace_bytes",
     "nkfb_infidelity_fwd", "nkfb_infidelity_grad", "nkfb_grad_finalize", "nkfb_chain_stats",
     "nkfb_renyi2", "nkfb_microbench", "nkfb_optimizer_update", "nkfb_set_option", "nkfb_weighted_score",
-    "nkfb_score_dot", "nkfb_grad_finalize_centred",
+    "nkfb_score_dot", "nkfb_grad_finalize_centred", "nkfb_tc_prepare",
 ]
 
 OPT_SAMPLER_ALGO = 1
 OPT_SAMPLER_SHARE = 2
 OPT_FWD_MAX_CTAS = 3
+OPT_TC_TABLES_VALID = 4
 SAMPLER_AUTO, SAMPLER_ADDITIVE, SAMPLER_MULTIPLICATIVE = 0, 1, 2
 
 
@@ -96,6 +97,7 @@ def load_library():
         lib.nkfb_renyi2.argtypes = [vp, P(RbmT), vp, i64, vp, P(dbl), vp, vp, vp, vp, vp]
         lib.nkfb_microbench.argtypes = [vp, i32, i32, P(dbl), vp]
         lib.nkfb_set_option.argtypes = [vp, i32, i64]
+        lib.nkfb_tc_prepare.argtypes = [vp, P(RbmT), P(RbmT), P(dbl), vp]
         lib.nkfb_weighted_score.argtypes = [vp, P(RbmT), vp, i64, P(dbl), vp, vp, vp]
         lib.nkfb_grad_finalize_centred.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
         lib.nkfb_score_dot.argtypes = [vp, P(RbmT), vp, i64, P(dbl), vp, vp, vp]
@@ -258,6 +260,20 @@ class Handle:
     def set_fwd_max_ctas(self, n):
         """Upper bound on the CTAs of the next tensor-core estimator launches (0: no limit); include/nkfb200.h."""
         self.set_option(OPT_FWD_MAX_CTAS, n)
+
+    def set_tc_tables_valid(self, flag):
+        """The tables of the tensor-core estimator / gradient kernels still match the parameter buffers (launches on the
+        same buffers skip their preparation kernels); clear it before the parameters change.  include/nkfb200.h."""
+        self.set_option(OPT_TC_TABLES_VALID, 1 if flag else 0)
+
+    def tc_prepare(self, psi: "RbmSpec", phi, local_states):
+        """Write the parameter tables of the tensor-core estimator (psi, phi) and gradient (psi) kernels on the current
+        stream, ahead of the launches that read them (nkfb_tc_prepare); phi may be None (gradient tables only)."""
+        self._on_device(psi.kernel, *([phi.kernel] if phi is not None else []))
+        a = psi.struct()
+        b = phi.struct() if phi is not None else None
+        self._check(self.lib.nkfb_tc_prepare(self.h, C.byref(a), C.byref(b) if b is not None else None,
+                                             _ls(local_states), self._stream()), "nkfb_tc_prepare")
 
     # ---------------------------------------------------------------- pack / unpack
     def pack(self, x, local_states):

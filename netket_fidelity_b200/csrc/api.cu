@@ -351,6 +351,10 @@ extern "C" int nkfb_set_option(nkfb_handle_t h, int key, int64_t value) {
       if (value < 0 || value > (1 << 20)) NKFB_FAIL(h, NKFB_ERR_INVALID, "estimator CTA limit must be >= 0");
       h->opt_fwd_max_ctas = (int)value;
       return NKFB_OK;
+    case NKFB_OPT_TC_TABLES_VALID:
+      if (value < 0 || value > 1) NKFB_FAIL(h, NKFB_ERR_INVALID, "tables-valid flag must be 0 or 1");
+      h->opt_tc_tables_valid = (int)value;
+      return NKFB_OK;
     default: NKFB_FAIL(h, NKFB_ERR_INVALID, "unknown option %d", key);
   }
 }

@@ -25,7 +25,20 @@ struct nkfb_handle_s {
   int opt_sampler_algo;  // NKFB_OPT_SAMPLER_ALGO
   int opt_sampler_share; // NKFB_OPT_SAMPLER_SHARE: sampler launches of equal size that run side by side (default 1)
   int opt_fwd_max_ctas;  // NKFB_OPT_FWD_MAX_CTAS: upper bound on the CTAs of the tensor-core estimator (0 = none)
+  int opt_tc_tables_valid;  // NKFB_OPT_TC_TABLES_VALID: the tables nkfb_tc_prepare wrote still match the parameters
+  // what nkfb_tc_prepare (or the last estimator / gradient launch) left in ws2 / ws3: parameter buffers and geometry
+  struct TcTablesKey {
+    const void *w[2], *b[2];
+    int n_visible, n_hidden, NN, NC, KC;
+  } tc_fwd_key, tc_grad_key;
 };
+
+namespace nkfb {
+inline bool tc_key_equal(const nkfb_handle_s::TcTablesKey &x, const nkfb_handle_s::TcTablesKey &y) {
+  return x.w[0] == y.w[0] && x.w[1] == y.w[1] && x.b[0] == y.b[0] && x.b[1] == y.b[1] && x.n_visible == y.n_visible &&
+         x.n_hidden == y.n_hidden && x.NN == y.NN && x.NC == y.NC && x.KC == y.KC && x.w[0] != nullptr;
+}
+}  // namespace nkfb
 
 // Every entry point runs on the handle's device whatever the caller's current device is, and restores the latter.
 struct NkfbDeviceGuard {

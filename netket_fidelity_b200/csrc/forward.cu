@@ -652,6 +652,27 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
                        const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
                        const void *rho1, const double *sums, double *grad_acc, cudaStream_t st,
                        const void *weights = nullptr);
+int tc_fwd_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const double ls[2], cudaStream_t st);
+int tc_grad_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const double ls[2], cudaStream_t st);
+}
+
+extern "C" int nkfb_tc_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,
+                               const double local_states[2], void *stream) {
+  if (!h) return NKFB_ERR_INVALID;
+  NKFB_DEVICE_GUARD(h);
+  NKFB_NVTX("nkfb_tc_prepare");
+  int rc = check_net(h, psi);
+  if (rc) return rc;
+  if (phi && (rc = check_net(h, phi))) return rc;
+  if (!local_states) NKFB_FAIL(h, NKFB_ERR_INVALID, "null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (phi && psi->n_visible == phi->n_visible && psi->dtype == phi->dtype) {
+    const char *impl = getenv("NKFB_FWD_IMPL");
+    if (!(impl && strcmp(impl, "simt") == 0) && (rc = nkfb::tc_fwd_prepare(h, psi, phi, local_states, st))) return rc;
+  }
+  const char *gimpl = getenv("NKFB_GRAD_IMPL");
+  if (!(gimpl && strcmp(gimpl, "simt") == 0) && (rc = nkfb::tc_grad_prepare(h, psi, local_states, st))) return rc;
+  return NKFB_OK;
 }
 
 extern "C" int nkfb_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi,

@@ -438,6 +438,74 @@ __global__ void __launch_bounds__(TC_FWD_THREADS, 2) infid_fwd_tc_kernel(NetDev<
   if (warp == 0) tmem_dealloc(tmem_d, a.tmem_cols);
 }
 
+// geometry of the tensor-core estimator for a pair of networks; false when the tensor-core path does not apply to them
+static bool tc_fwd_geometry(const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, TcGeom *g, size_t *smem_out) {
+  if (psi->dtype != NKFB_F32 || phi->dtype != NKFB_F32) return false;
+  if (psi->n_hidden != phi->n_hidden || psi->n_visible != phi->n_visible) return false;
+  // two CTAs per SM (each its own TMEM accumulator): one CTA's UMMAs and X-tile builds overlap the other's
+  // log-cosh epilogue; the W~ chunk of a CTA is sized for half of the shared memory
+  size_t budget = 104 * 1024;
+  if (const char *e = getenv("NKFB_TC_FWD_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
+  const size_t xb = (size_t)(((psi->n_visible + 1 + 15) / 16) * 2) * TC_ROWS * 16 + 4096;  // X tile + spin-group table
+  if (!tc_geometry(psi->n_visible, psi->n_hidden, g, 2 * psi->n_hidden, 0, xb, budget) &&
+      !tc_geometry(psi->n_visible, psi->n_hidden, g, 2 * psi->n_hidden, 0, xb))
+    return false;
+  const size_t smem = g->b_chunk_bytes() + g->a_bytes() + 4096 + (size_t)g->NN * 16 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
+  if (smem > 227 * 1024) return false;
+  *smem_out = smem;
+  return true;
+}
+
+static nkfb_handle_s::TcTablesKey tc_fwd_key_of(const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const TcGeom &g) {
+  nkfb_handle_s::TcTablesKey k;
+  k.w[0] = psi->kernel;
+  k.w[1] = phi->kernel;
+  k.b[0] = psi->bias;
+  k.b[1] = phi->bias;
+  k.n_visible = psi->n_visible;
+  k.n_hidden = psi->n_hidden;
+  k.NN = g.NN;
+  k.NC = g.NC;
+  k.KC = g.KC;
+  return k;
+}
+
+// The bf16 splits of both networks (the handle's second workspace).  With NKFB_OPT_TC_TABLES_VALID set and the tables of
+// these very parameter buffers and geometry already there (nkfb_tc_prepare, or an earlier estimator launch), nothing is
+// launched: `force` = false is the estimator's own call, true is nkfb_tc_prepare's.
+static int tc_fwd_tables(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const TcGeom &g, bool force,
+                         cudaStream_t st) {
+  const size_t need = 2 * g.prep_bytes_per_net();
+  if (h->ws2_bytes < need) {
+    if (h->ws2) cudaFree(h->ws2);
+    h->ws2 = nullptr;
+    h->ws2_bytes = 0;
+    h->tc_fwd_key.w[0] = nullptr;
+    NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws2, need));
+    h->ws2_bytes = need;
+  }
+  const nkfb_handle_s::TcTablesKey key = tc_fwd_key_of(psi, phi, g);
+  if (!force && h->opt_tc_tables_valid && tc_key_equal(h->tc_fwd_key, key)) return NKFB_OK;
+  __nv_bfloat16 *prep_psi = (__nv_bfloat16 *)h->ws2;
+  __nv_bfloat16 *prep_phi = (__nv_bfloat16 *)((char *)h->ws2 + g.prep_bytes_per_net());
+  const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
+  const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+  tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, prep_psi);
+  NKFB_LAUNCHED(h);
+  tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(phi), g, prep_phi);
+  NKFB_LAUNCHED(h);
+  h->tc_fwd_key = key;
+  return NKFB_OK;
+}
+
+// nkfb_tc_prepare, estimator half: returns NKFB_OK (also when the tensor-core path does not apply: nothing to prepare)
+int tc_fwd_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const double ls[2], cudaStream_t st) {
+  TcGeom g;
+  size_t smem;
+  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1]) || !tc_fwd_geometry(psi, phi, &g, &smem)) return NKFB_OK;
+  return tc_fwd_tables(h, psi, phi, g, true, st);
+}
+
 // returns NKFB_OK, an error, or 1 when the tensor-core path does not apply (caller falls back to the SIMT kernel)
 int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *phi, const nkfb_op_t *op1,
                       const nkfb_op_t *op2, const nkfb_op_t *op4, const uint32_t *sigma, const uint32_t *eta,
@@ -451,36 +519,14 @@ int tc_infidelity_fwd(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_rbm_t *
   if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
   if (S < 2048) return 1;
   TcGeom g;
-  // two CTAs per SM (each its own TMEM accumulator): one CTA's UMMAs and X-tile builds overlap the other's
-  // log-cosh epilogue; the W~ chunk of a CTA is sized for half of the shared memory
-  size_t budget = 104 * 1024;
-  if (const char *e = getenv("NKFB_TC_FWD_BUDGET_KB")) budget = (size_t)atoi(e) * 1024;
-  const size_t xb = (size_t)(((psi->n_visible + 1 + 15) / 16) * 2) * TC_ROWS * 16 + 4096;  // X tile + spin-group table
-  if (!tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb, budget) &&
-      !tc_geometry(psi->n_visible, psi->n_hidden, &g, 2 * psi->n_hidden, 0, xb))
-    return 1;
-  const size_t smem = g.b_chunk_bytes() + g.a_bytes() + 4096 + (size_t)g.NN * 16 + 7 * TC_ROWS * sizeof(cx<float>) + 128;
-  if (smem > 227 * 1024) return 1;
-
-  // prepared bf16 splits of both networks live in the handle's second workspace
-  const size_t need = 2 * g.prep_bytes_per_net();
-  if (h->ws2_bytes < need) {
-    if (h->ws2) cudaFree(h->ws2);
-    h->ws2 = nullptr;
-    h->ws2_bytes = 0;
-    NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws2, need));
-    h->ws2_bytes = need;
+  size_t smem;
+  if (!tc_fwd_geometry(psi, phi, &g, &smem)) return 1;
+  {
+    const int rc = tc_fwd_tables(h, psi, phi, g, false, st);
+    if (rc != NKFB_OK) return rc;
   }
   __nv_bfloat16 *prep_psi = (__nv_bfloat16 *)h->ws2;
   __nv_bfloat16 *prep_phi = (__nv_bfloat16 *)((char *)h->ws2 + g.prep_bytes_per_net());
-  {
-    const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
-    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
-    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, prep_psi);
-    NKFB_LAUNCHED(h);
-    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(phi), g, prep_phi);
-    NKFB_LAUNCHED(h);
-  }
   TcFwdArgs a;
   a.op1 = make_opdev(op1);
   a.op2 = make_opdev(op2);

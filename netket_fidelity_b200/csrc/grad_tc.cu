@@ -429,17 +429,12 @@ __global__ void __launch_bounds__(NT + 32, 1) infid_grad_tc_kernel(NetDev<float>
   if (warp == 0) tmem_dealloc(tmem_base_sh, 512);
 }
 
-// returns NKFB_OK, an error, or 1 when the tensor-core path does not apply
-int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
-                       const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
-                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st, const void *weights) {
-  if (psi->dtype != NKFB_F32) return 1;
-  if (op2 && op2->kind == NKFB_OP_ISING) return 1;
-  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
-  if (S < 2048) return 1;
+// geometry of the tensor-core gradient for a network; false when the tensor-core path does not apply to it
+static bool tc_grad_geometry(const nkfb_rbm_t *psi, TcGeom *gp, bool *wide_out, size_t *smem_out) {
+  if (psi->dtype != NKFB_F32) return false;
   const int N = psi->n_visible, M = psi->n_hidden;
-  if (N + 1 > TC_ROWS) return 1;  // GEMM 2 holds all gradient rows (spins + bias) in one UMMA M = 128 tile
-  TcGeom g;
+  if (N + 1 > TC_ROWS) return false;  // GEMM 2 holds all gradient rows (spins + bias) in one UMMA M = 128 tile
+  TcGeom &g = *gp;
   // per column: three bf16 splits of a 128-sample Y tile (768 B) + gate row + correction (8 B); fixed: two X tiles, the
   // spin-group table, two tiles of per-sample weights.  Four accumulators of NN columns share the 512 TMEM columns.
   const size_t fixed = 2 * (size_t)GX_CHUNKS * TC_ROWS * 16 + 4096 + 2 * 3 * TC_ROWS * sizeof(cx<float>);
@@ -449,23 +444,67 @@ int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *
   // sixteen warps (chunks of a multiple of 32 columns, up to 128) when that geometry fits; else eight (multiples of 16, up to 128: four accumulators of NN columns share the 512 TMEM columns)
   bool wide = !getenv("NKFB_GRAD_TC_NARROW") &&
               tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 32, 128) && smem_of(g) <= (size_t)226 * 1024;
-  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 16, 128)) return 1;
+  if (!wide && !tc_geometry(N, M, &g, 2 * (M + 1), 3 * TC_ROWS * 2 + 8, fixed, 226 * 1024, 16, 128)) return false;
   const size_t smem = smem_of(g);
-  if (smem > 227 * 1024) return 1;
+  if (smem > 227 * 1024) return false;
+  *wide_out = wide;
+  *smem_out = smem;
+  return true;
+}
 
+// The bf16 splits of the network (the handle's third workspace); see tc_fwd_tables (forward_tc.cu) for `force` and
+// NKFB_OPT_TC_TABLES_VALID.
+static int tc_grad_tables(nkfb_handle_t h, const nkfb_rbm_t *psi, const TcGeom &g, bool force, cudaStream_t st) {
   const size_t need = g.prep_bytes_per_net();
   if (h->ws3_bytes < need) {
     if (h->ws3) cudaFree(h->ws3);
     h->ws3 = nullptr;
     h->ws3_bytes = 0;
+    h->tc_grad_key.w[0] = nullptr;
     NKFB_CHECK_CUDA(h, cudaMalloc(&h->ws3, need));
     h->ws3_bytes = need;
   }
+  nkfb_handle_s::TcTablesKey key;
+  key.w[0] = key.w[1] = psi->kernel;
+  key.b[0] = key.b[1] = psi->bias;
+  key.n_visible = psi->n_visible;
+  key.n_hidden = psi->n_hidden;
+  key.NN = g.NN;
+  key.NC = g.NC;
+  key.KC = g.KC;
+  if (!force && h->opt_tc_tables_valid && tc_key_equal(h->tc_grad_key, key)) return NKFB_OK;
+  const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
+  const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
+  tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, (__nv_bfloat16 *)h->ws3);
+  NKFB_LAUNCHED(h);
+  h->tc_grad_key = key;
+  return NKFB_OK;
+}
+
+// nkfb_tc_prepare, gradient half: returns NKFB_OK (also when the tensor-core path does not apply: nothing to prepare)
+int tc_grad_prepare(nkfb_handle_t h, const nkfb_rbm_t *psi, const double ls[2], cudaStream_t st) {
+  TcGeom g;
+  bool wide;
+  size_t smem;
+  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1]) || !tc_grad_geometry(psi, &g, &wide, &smem)) return NKFB_OK;
+  return tc_grad_tables(h, psi, g, true, st);
+}
+
+// returns NKFB_OK, an error, or 1 when the tensor-core path does not apply
+int tc_infidelity_grad(nkfb_handle_t h, const nkfb_rbm_t *psi, const nkfb_op_t *op2, const uint32_t *sigma,
+                       const uint32_t *eta, int64_t S, const double ls[2], double cv, const void *log_val,
+                       const void *rho1, const double *sums, double *grad_acc, cudaStream_t st, const void *weights) {
+  if (psi->dtype != NKFB_F32) return 1;
+  if (op2 && op2->kind == NKFB_OP_ISING) return 1;
+  if (!bf16_exact(ls[0]) || !bf16_exact(ls[1])) return 1;
+  if (S < 2048) return 1;
+  TcGeom g;
+  bool wide;
+  size_t smem;
+  if (!tc_grad_geometry(psi, &g, &wide, &smem)) return 1;
   {
-    const int64_t tot = (int64_t)g.NC * g.KC * g.NN;
-    const int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)h->sm_count * 8);
-    tc_prep_kernel<<<grid, 256, 0, st>>>(make_netdev<float>(psi), g, (__nv_bfloat16 *)h->ws3);
-    NKFB_LAUNCHED(h);
+    const int rc = tc_grad_tables(h, psi, g, false, st);
+    if (rc != NKFB_OK) return rc;
   }
   TcGradArgs a;
   a.op2 = make_opdev(op2);

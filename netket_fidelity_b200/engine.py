@@ -171,6 +171,12 @@ class InfidelityStep:
         for st in (self.psi_stream, self.side_stream, self.est_stream):
             st.wait_stream(main)
         idle = max(1, self._idle_sms())
+        # the parameter tables of pass B are written ahead of pass A of the first segment (on the estimator's stream, under
+        # the sampling of the second one), those of pass A by its first launch: pass A of the LAST segment and pass B --
+        # the exposed ones -- launch without their preparation kernels (NKFB_OPT_TC_TABLES_VALID; estimate() clears it).  The
+        # earlier pass A launches keep theirs on purpose: those few microseconds let the sampler CTAs of the next segment
+        # (high-priority streams, one per SM) take their SMs before the estimator CTAs spread over the idle ones --
+        # without them the estimator got there first and 20 sampler CTAs waited for it (8-GPU shard 6.02 -> 7.36 ms).
         self.h.set_sampler_share(2)
         try:
             for k in range(K):
@@ -192,10 +198,16 @@ class InfidelityStep:
                 with torch.cuda.stream(self.est_stream):
                     # two estimator CTAs per idle SM while a sampler segment is still to come; the last one has the GPU
                     self.h.set_fwd_max_ctas(2 * idle if k < K - 1 else 0)
+                    self.h.set_tc_tables_valid(k == K - 1)
+                    if k == 0:
+                        self.h.tc_prepare(psi, None, cfg.local_states)
                     sl = slice(k * S_seg, (k + 1) * S_seg)
                     self.h.infidelity_fwd(psi, phi, self.sigma[k].view(-1, self.W32), self.eta[k].view(-1, self.W32),
                                           cfg.local_states, cfg.cv_coeff, self.op1, self.op2, self.op4, sums=self.sums,
                                           out=(self._lv[sl], self._L[sl], self._rho1[sl]))
+        except BaseException:
+            self.h.set_tc_tables_valid(False)
+            raise
         finally:
             self.h.set_sampler_share(1)
             self.h.set_fwd_max_ctas(0)
@@ -246,6 +258,12 @@ class InfidelityStep:
     def estimate(self, psi, phi, return_grad=True, events=None):
         """Pass A (+ pass B).  Returns (sums[8] device tensor, L (S_local,), grad (P,) complex | None).
         `events`: optional 3 CUDA events recorded before pass A, after pass A, after pass B (bench.py)."""
+        try:
+            return self._estimate(psi, phi, return_grad, events)
+        finally:
+            self.h.set_tc_tables_valid(False)     # set by _sample_streamed for the launches of this step only
+
+    def _estimate(self, psi, phi, return_grad, events):
         cfg = self.cfg
         sig = self.sigma.view(-1, self.W32)
         eta = self.eta.view(-1, self.W32)

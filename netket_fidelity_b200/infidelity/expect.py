@@ -89,6 +89,7 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
     psi, phi = vstate._spec(), target._spec()
     ls = vstate._ls
     fresh = vstate._samples_packed is None and target._samples_packed is None and target is not vstate
+    tables_flag = False
     idle = _streamed_idle_sms(vstate, target) if fresh else 0
     if idle:
         # A shard whose sampler launches leave SMs idle (one rank of a 4- / 8-GPU C4 job): sample in two segments and run
@@ -124,13 +125,22 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
                     rho1 = torch.empty_like(log_val)
                     L_seg = torch.empty((K * S_seg,), dtype=torch.float32, device=dev)
                     s_est.wait_stream(main)
+                    tables_flag = True
                 s_est.wait_stream(s_psi)
                 s_est.wait_stream(s_phi)
                 with torch.cuda.stream(s_est):
                     h.set_fwd_max_ctas(2 * idle if k < K - 1 else 0)
+                    # pass B's tables ahead of the first pass A; pass A of the last segment reuses the first one's
+                    # (engine.py: the earlier pass A launches keep their preparation kernels on purpose)
+                    h.set_tc_tables_valid(k == K - 1)
+                    if k == 0:
+                        h.tc_prepare(psi, None, ls)
                     sl = slice(k * S_seg, (k + 1) * S_seg)
                     h.infidelity_fwd(psi, phi, sig_seg[k].view(-1, W32), eta_seg[k].view(-1, W32), ls, op.cv_coeff, op1, op2,
                                      op4, sums=sums, out=(log_val[sl], L_seg[sl], rho1[sl]))
+        except BaseException:
+            h.set_tc_tables_valid(False)
+            raise
         finally:
             h.set_sampler_share(1)
             h.set_fwd_max_ctas(0)
@@ -166,15 +176,20 @@ def infidelity_expect(vstate: MCState, op, return_grad: bool):
         chain_len = eta.shape[-2]
         sigma, eta = sigma.view(-1, W32), eta.view(-1, W32)
         log_val, L, rho1, _ = h.infidelity_fwd(psi, phi, sigma, eta, ls, op.cv_coeff, op1, op2, op4, sums=sums)
-    _allreduce(sums)
-    # n_chains = sigma_t.shape[-2] (overlap/expect.py:72): the reference hands the CHAIN LENGTH to
-    # nkjax.expect as "n_chains"; mean, variance and gradient do not depend on it
-    # the statistics kernels go into the stream here; their read-back (a host synchronisation) waits until the
-    # gradient has been enqueued behind them, so that the GPU does not idle while the host does the statistics
-    stats_ctx = vstate._stats_begin(L, chain_len, sums=sums)
     flat = None
+    try:
+        _allreduce(sums)
+        # n_chains = sigma_t.shape[-2] (overlap/expect.py:72): the reference hands the CHAIN LENGTH to
+        # nkjax.expect as "n_chains"; mean, variance and gradient do not depend on it
+        # the statistics kernels go into the stream here; their read-back (a host synchronisation) waits until the
+        # gradient has been enqueued behind them, so that the GPU does not idle while the host does the statistics
+        stats_ctx = vstate._stats_begin(L, chain_len, sums=sums)
+        if return_grad:
+            h.infidelity_grad(psi, sigma, eta, ls, op.cv_coeff, log_val, rho1, sums, op2=op2, grad_acc=gacc)
+    finally:
+        if tables_flag:
+            h.set_tc_tables_valid(False)     # set by the streamed branch for the launches of this call only
     if return_grad:
-        h.infidelity_grad(psi, sigma, eta, ls, op.cv_coeff, log_val, rho1, sums, op2=op2, grad_acc=gacc)
         _allreduce(gacc)
         flat = h.grad_finalize(gacc, sums, vstate._flat.numel(), vstate._cdtype)
     F_stats = vstate._stats_end(stats_ctx, L)

@@ -126,3 +126,51 @@ def test_tc_estimator_large_imaginary_preactivations(h, B):
     finally:
         os.environ.pop("NKFB_FWD_IMPL", None)
     assert rel_err(out["tc"], out["simt"]) <= tol, rel_err(out["tc"], out["simt"])
+
+
+@pytest.mark.parametrize("N,M,S,std", [(100, 400, 4096, 0.01), (20, 40, 2304, 0.05)])
+def test_tc_prepared_tables(h, N, M, S, std):
+    """nkfb_tc_prepare + NKFB_OPT_TC_TABLES_VALID: the estimator and the gradient launch without their three preparation
+    kernels and give bit-identical per-sample results (same tables, same kernels); with the flag set but OTHER parameter
+    buffers the tables are re-prepared (the flag is a promise about the buffers they were written from, nothing else);
+    after the flag is cleared an in-place parameter update is seen again."""
+    rng = np.random.default_rng(3)
+    psi, phi = _net(N, M, 1234, std), _net(N, M, 5678, std)
+    sigma, eta = rng.choice([-1.0, 1.0], (S, N)), rng.choice([-1.0, 1.0], (S, N))
+    sp, ep = packed_to_torch(pack_np(sigma)), packed_to_torch(pack_np(eta))
+    a, b = to_rbmspec(psi, torch.complex64), to_rbmspec(phi, torch.complex64)
+    U, Ud = to_opspec(oops.Rx(N, 1, 0.2)), to_opspec(oops.Rx(N, 1, -0.2))
+
+    def run(x, y):
+        n0 = h.launches
+        lv, L, rho1, sums = h.infidelity_fwd(x, y, sp, ep, LS, -0.5, U, Ud, None)
+        gacc = h.infidelity_grad(x, sp, ep, LS, -0.5, lv, rho1, sums, Ud)
+        torch.cuda.synchronize()
+        return L.clone(), lv.clone(), gacc.clone(), h.launches - n0
+
+    L0, lv0, g0, n_plain = run(a, b)
+    try:
+        h.tc_prepare(a, b, LS)
+        h.set_tc_tables_valid(True)
+        L1, lv1, g1, n_prep = run(a, b)
+        assert n_prep == n_plain - 3, (n_plain, n_prep)
+        assert torch.equal(L0, L1) and torch.equal(lv0, lv1)
+        assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) <= 1e-7       # order of the atomic adds only (measured 4e-9)
+        # other buffers under the same flag: prepared again, results of THOSE parameters
+        a2, b2 = to_rbmspec(phi, torch.complex64), to_rbmspec(psi, torch.complex64)
+        L2, lv2, g2, n2 = run(a2, b2)
+        assert n2 == n_plain
+        h.set_tc_tables_valid(False)
+        L2r, lv2r, g2r, _ = run(a2, b2)
+        assert torch.equal(L2, L2r) and torch.equal(lv2, lv2r)
+        assert not torch.equal(L2, L0)
+        # the tables now belong to (a2, b2); with the flag set again (a, b) is re-prepared, not served from them
+        h.set_tc_tables_valid(True)
+        L3, lv3, g3, n3 = run(a, b)
+        assert n3 == n_plain and torch.equal(L3, L0)
+    finally:
+        h.set_tc_tables_valid(False)
+    # flag cleared: an in-place update of the same buffers is seen
+    a.kernel.mul_(1.5)
+    L4, _, _, n4 = run(a, b)
+    assert n4 == n_plain and not torch.equal(L4, L0)
