@@ -26,6 +26,16 @@ from .. import _native as nv
 from .. import parallel as par
 from .stats import Stats, stats_from_partials
 
+_readback_streams = {}
+
+
+def _readback_stream(dev):
+    """One side stream per device for the asynchronous read-back of the chain statistics (`MCState._stats_begin`)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _readback_streams:
+        _readback_streams[key] = torch.cuda.Stream(device=dev)
+    return _readback_streams[key]
+
 _seed_counter = itertools.count()
 
 
@@ -318,7 +328,11 @@ class MCState(_RBMStateBase):
 
     def _stats_begin(self, L, n_chains_arg, sums=None):
         """Device half of `_stats_of`: enqueues the partial-sum kernel (and the all-gather of the other ranks' rows)
-        without waiting for it, so that a caller can put more GPU work behind it before `_stats_end` reads back."""
+        and their read-back WITHOUT waiting for either, so that a caller can put more GPU work behind them before
+        `_stats_end` synchronises.  The read-back (partial sums and `sums` into pinned host memory) runs on a side
+        stream ordered after the kernels above: `_stats_end` waits for that copy only -- not for what the caller has
+        enqueued on the main stream in between (pass B of an infidelity step), under which the host then does the
+        chain statistics."""
         S = L.numel()
         rows = int(n_chains_arg)
         cols = S // rows
@@ -331,16 +345,53 @@ class MCState(_RBMStateBase):
             from ..parallel import allgather_rows
             part = allgather_rows(part)
             rows = rows * self._world
-        return part, rows, cols, l_block, n_blocks, sums
+        host = None
+        if part.is_cuda:
+            main = torch.cuda.current_stream(part.device)
+            side = _readback_stream(part.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                part_h = self._pinned_like("part", part)
+                part_h.copy_(part, non_blocking=True)
+                sums_h = None
+                if torch.is_tensor(sums) and sums.is_cuda:
+                    sums_h = self._pinned_like("sums", sums)
+                    sums_h.copy_(sums, non_blocking=True)
+                    sums.record_stream(side)
+                done = torch.cuda.Event()
+                done.record(side)
+            part.record_stream(side)
+            host = (part_h, sums_h, done)
+        return part, rows, cols, l_block, n_blocks, sums, host
+
+    def _pinned_like(self, name, t):
+        """A pinned host buffer of the shape / dtype of `t`, kept per state and purpose (reused from step to step: the
+        previous content has been consumed by `_stats_end` before the next `_stats_begin` overwrites it)."""
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        b = cache.get(name)
+        if b is None or b.shape != t.shape or b.dtype != t.dtype:
+            b = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            cache[name] = b
+        return b
 
     def _stats_end(self, ctx, L):
-        """Host half of `_stats_of` (synchronises with the stream)."""
-        part, rows, cols, l_block, n_blocks, sums = ctx
+        """Host half of `_stats_of` (waits for the read-back enqueued by `_stats_begin`, not for the whole stream)."""
+        part, rows, cols, l_block, n_blocks, sums, host = ctx
         S = L.numel()
-        part = part.cpu().numpy()
+        s_host = None
+        if host is not None:
+            part_h, sums_h, done = host
+            done.synchronize()
+            part = part_h.numpy()
+            s_host = sums_h.numpy() if sums_h is not None else None
+        else:
+            part = part.cpu().numpy()
         tot, tot2 = float(part[:, 0].sum()), None
         if sums is not None:
-            s = sums.cpu().numpy() if torch.is_tensor(sums) else np.asarray(sums)
+            if s_host is not None:
+                s = s_host
+            else:
+                s = sums.cpu().numpy() if torch.is_tensor(sums) else np.asarray(sums)
             n_glob = s[4]
             mean = s[0] / n_glob
             var = max(0.0, s[1] / n_glob - mean * mean)

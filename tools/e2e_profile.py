@@ -61,3 +61,25 @@ for _ in range(20):
     e2e_step()
 pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+
+# host timeline of one step (the GPU is idle from the synchronize that ends a step until the first sampler launch of the next)
+import numpy as np  # noqa: E402
+seg = []
+for _ in range(20):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vs_psi.parameters = pin_tree["psi"]
+    I_op.target.parameters = pin_tree["phi"]
+    t1 = time.perf_counter()
+    vs_psi.reset()
+    I_op.target.reset()
+    t2 = time.perf_counter()
+    st, grad = vs_psi.expect_and_grad(I_op)
+    t3 = time.perf_counter()
+    grad_host.copy_(vs_psi._last_flat_grad, non_blocking=True)
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    seg.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+m = 1e3 * np.median(np.array(seg), axis=0)
+print(f"host timeline (ms, median of 20): set parameters {m[0]:.3f} | reset {m[1]:.3f} | expect_and_grad {m[2]:.3f} | "
+      f"gradient D2H + synchronize {m[3]:.3f} | total {m.sum():.3f}")
