@@ -116,3 +116,28 @@ def test_convergence_stopping():
     cb = ConvergenceStopping(1e-3, smoothing_window=2, patience=2)
     cont = [cb(i, {"Infidelity": Stats(mean=v)}, D()) for i, v in enumerate([1.0, 1e-4, 1e-4, 1e-4, 1e-4, 1e-4])]
     assert cont[:4] == [True, True, True, True] and cont[-1] is False
+
+
+def test_bench_subtracts_the_l2_flushes_from_the_bracket():
+    """bench.net_of_flushes: K steps bracketed by one pair of events, K flushes between them timed by their own pairs;
+    the step time is the bracket minus K x the median flush (a host hiccup inside one flush interval is not subtracted),
+    the raw bracket and the flush are reported beside it."""
+    import bench
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    class Ctx:
+        def max_over_ranks(self, x):
+            return x
+
+    flushes = [(Ev(0.0), Ev(0.05)), (Ev(10.0), Ev(10.05)), (Ev(20.0), Ev(20.95)), (Ev(30.0), Ev(30.05)), (Ev(40.0), Ev(40.05))]
+    net, bracket, flush = bench.net_of_flushes(Ctx(), Ev(0.0), Ev(50.0), flushes)
+    assert abs(flush - 0.05) < 1e-12 and bracket == 50.0
+    assert abs(net - (50.0 - 5 * 0.05)) < 1e-12
+    net0, bracket0, flush0 = bench.net_of_flushes(Ctx(), Ev(0.0), Ev(7.0), [])
+    assert (net0, bracket0, flush0) == (7.0, 7.0, 0.0)
