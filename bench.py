@@ -481,7 +481,11 @@ def run_b200(args):
     ctx.barrier()
     e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
     h2d = sum(p.numel() * p.element_size() for k in pinned for p in pinned[k] if p is not None)
-    d2h = grad_host.numel() * grad_host.element_size() + 64
+    # gradient + the 8 sums + the chain-statistics partial sums MCState reads back (rows x (3 + n_blocks) doubles with
+    # rows = chain_length on every rank, as the reference hands it to nkjax.expect; all ranks' rows after the all-gather)
+    st_rows, st_cols = w["chain_length"], w["n_chains"] // world
+    st_blocks = st_cols // max(1, st_cols // 32)
+    d2h = grad_host.numel() * grad_host.element_size() + 64 + st_rows * world * (3 + st_blocks) * 8
     del vs_psi, vs_phi, I_op
 
     # ------------------------------------------------------------ the same C4 step in complex128 ("f64") and the other
